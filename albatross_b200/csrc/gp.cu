@@ -1,0 +1,958 @@
+// GP-level orchestration and the extern "C" surface declared in include/albatross_b200.h.
+//
+// Each entry point cites the reference routine it replaces in the header; this file only sequences
+// device kernels (gram.cu, gemm.cu, linalg.cu) on the handle's stream and moves results to the host.
+#include "gram.cuh"
+#include "linalg.cuh"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+namespace ab {
+
+int gram_sym_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *feats, uint32_t flags,
+                    ab_matrix_s **out);
+int gram_cross_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *fx,
+                      const ab_matrix_s *fy, ab_matrix_s **out);
+int gram_diag_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *feats, double *d_out);
+int upload_features(ab_handle_s *h, const double *feats, int64_t n, int dim, ab_matrix_s **out);
+
+namespace {
+
+// RAII for temporaries so that every early return recycles device buffers.
+struct Scope {
+  explicit Scope(ab_handle_s *h) : h(h) {}
+  ~Scope() {
+    for (auto *m : mats) {
+      matrix_delete(h, m);
+    }
+    for (auto &b : bufs) {
+      dev_release(h, b.first, b.second);
+    }
+  }
+  ab_matrix_s *own(ab_matrix_s *m) {
+    mats.push_back(m);
+    return m;
+  }
+  void disown(ab_matrix_s *m) { mats.erase(std::remove(mats.begin(), mats.end(), m), mats.end()); }
+  int alloc(size_t bytes, void **out) {
+    int s = dev_alloc(h, bytes, out);
+    if (s == AB_OK) {
+      bufs.emplace_back(*out, bytes);
+    }
+    return s;
+  }
+  ab_handle_s *h;
+  std::vector<ab_matrix_s *> mats;
+  std::vector<std::pair<void *, size_t>> bufs;
+};
+
+MatView view(const ab_matrix_s *m) { return MatView{m->d, m->ld}; }
+
+int upload_bytes(ab_handle_s *h, Scope &sc, const void *host, size_t bytes, void **dev) {
+  AB_TRY(sc.alloc(bytes, dev));
+  if (bytes > 0) {
+    AB_CUDA(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  return AB_OK;
+}
+
+int download_bytes(ab_handle_s *h, const void *dev, size_t bytes, void *host) {
+  if (bytes > 0) {
+    AB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  }
+  AB_CUDA(cudaStreamSynchronize(h->stream));
+  return AB_OK;
+}
+
+int new_factor(ab_handle_s *h, ab_matrix_s *m, ab_factor_s **out) {
+  AB_REQUIRE(m->rows == m->cols, "factorisation needs a square matrix");
+  auto *f = new ab_factor_s();
+  f->m = m;
+  f->n = m->rows;
+  const int64_t nblocks = (f->n + LEAF - 1) / LEAF;
+  f->dinv_bytes = static_cast<size_t>(nblocks < 1 ? 1 : nblocks) * LEAF * LEAF * sizeof(double);
+  void *p = nullptr;
+  int s = dev_alloc(h, f->dinv_bytes, &p);
+  if (s != AB_OK) {
+    delete f;
+    return s;
+  }
+  f->dinv = static_cast<double *>(p);
+  *out = f;
+  return AB_OK;
+}
+
+void delete_factor(ab_handle_s *h, ab_factor_s *f) {
+  if (f == nullptr) {
+    return;
+  }
+  matrix_delete(h, f->m);
+  dev_release(h, f->dinv, f->dinv_bytes);
+  delete f;
+}
+
+// Factor `m` in place (consumed) and report the first bad pivot.
+int factorize(ab_handle_s *h, ab_matrix_s *m, ab_factor_s **out) {
+  ab_factor_s *f = nullptr;
+  int s = new_factor(h, m, &f);
+  if (s != AB_OK) {
+    matrix_delete(h, m);
+    return s;
+  }
+  h->h_flags[0] = INT_MAX;
+  cudaMemcpyAsync(h->d_flags, h->h_flags, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+  s = potrf(h, view(m), f->n, f->dinv, h->d_flags);
+  if (s == AB_OK) {
+    cudaError_t e =
+        cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) {
+      e = cudaStreamSynchronize(h->stream);
+    }
+    if (e != cudaSuccess) {
+      set_error("factorisation failed: %s", cudaGetErrorString(e));
+      s = AB_ERR_CUDA;
+    }
+  }
+  if (s != AB_OK) {
+    delete_factor(h, f);
+    return s;
+  }
+  f->bad_pivot = h->h_flags[0] == INT_MAX ? -1 : h->h_flags[0];
+  *out = f;
+  if (f->bad_pivot >= 0) {
+    set_error("matrix is not positive definite: pivot %lld is <= 0 or NaN",
+              static_cast<long long>(f->bad_pivot));
+    return AB_ERR_NOT_PD;
+  }
+  return AB_OK;
+}
+
+int require_usable(const ab_factor_s *f) {
+  AB_REQUIRE(f != nullptr && f->m != nullptr, "null factor");
+  if (f->bad_pivot >= 0) {
+    set_error("factor is not usable: matrix was not positive definite (pivot %lld)",
+              static_cast<long long>(f->bad_pivot));
+    return AB_ERR_NOT_PD;
+  }
+  return AB_OK;
+}
+
+// W <- L^-1 (lower triangular, W's strict upper triangle must already be zero).
+// T: workspace of at least ceil(n/2) x ceil(n/2) (+LEAF slack) doubles with leading dimension ldt.
+int trtri_rec(ab_handle_s *h, MatView L, const double *dinv, int64_t n, MatView W, MatView T) {
+  if (n <= LEAF) {
+    AB_CUDA(cudaMemcpy2DAsync(W.p, W.ld * sizeof(double), dinv, LEAF * sizeof(double),
+                              n * sizeof(double), n, cudaMemcpyDeviceToDevice, h->stream));
+    return AB_OK;
+  }
+  int64_t n1 = round_up((n + 1) / 2, LEAF);
+  if (n1 >= n) {
+    n1 = round_up(n, LEAF) - LEAF;
+  }
+  const int64_t n2 = n - n1;
+  AB_TRY(trtri_rec(h, L, dinv, n1, W, T));
+  AB_TRY(trtri_rec(h, L.sub(n1, n1), dinv + (n1 / LEAF) * LEAF * LEAF, n2, W.sub(n1, n1), T));
+  // W21 = -W22 * (L21 * W11)
+  AB_TRY(gemm(h, 0u, n2, n1, n1, 1., L.sub(n1, 0), W, 0., T));
+  return gemm(h, 0u, n2, n1, n2, -1., W.sub(n1, n1), T, 0., W.sub(n1, 0));
+}
+
+int inverse_factor(ab_handle_s *h, Scope &sc, const ab_factor_s *f, ab_matrix_s **Wout) {
+  const int64_t n = f->n;
+  ab_matrix_s *W = nullptr;
+  AB_TRY(matrix_new(h, n, n, &W));
+  sc.own(W);
+  AB_TRY(fill(h, view(W), n, n, 0.));
+  const int64_t half = round_up((n + 1) / 2, LEAF) + LEAF;
+  ab_matrix_s *T = nullptr;
+  AB_TRY(matrix_new(h, half, half, &T));
+  sc.own(T);
+  AB_TRY(trtri_rec(h, view(f->m), f->dinv, n, view(W), view(T)));
+  *Wout = W;
+  return AB_OK;
+}
+
+__global__ void gather_cols_kernel(const double *W, int64_t ldw, int64_t row0, int64_t rows,
+                                   const int64_t *idx, double *G, int64_t ldg) {
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (r < rows) {
+    G[r + c * ldg] = W[row0 + r + idx[c] * ldw];
+  }
+}
+
+__global__ void gather_vec_kernel(const double *v, const int64_t *idx, int64_t k, double *out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < k) {
+    out[i] = v[idx[i]];
+  }
+}
+
+// mean[idx[i]] = y[idx[i]] - x[i]; optional var[idx[i]] = diag[i]
+__global__ void heldout_scatter_kernel(const double *y, const double *x, const double *diag,
+                                       const int64_t *idx, int64_t k, double *mean, double *var) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < k) {
+    const int64_t t = idx[i];
+    mean[t] = y[t] - x[i];
+    if (var != nullptr) {
+      var[t] = diag[i];
+    }
+  }
+}
+
+// Leave-one-out: a_i = (K^-1)_ii; variance 1/a_i, mean y_i - information_i / a_i
+// (cross_validation_utils.hpp:172-197 with 1x1 blocks).  per-point score terms written to `terms`.
+__global__ void loo_kernel(const double *a, const double *y, const double *info, int64_t n,
+                           double *mean, double *var, double *terms) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    const double variance = 1. / a[i];
+    const double x = info[i] * variance;
+    mean[i] = y[i] - x;
+    var[i] = variance;
+    // univariate NLL of deviation x under `variance` (stats/gaussian.hpp:19-23)
+    terms[i] = x * x / (2. * variance) + 0.5 * log(2. * M_PI * variance);
+  }
+}
+
+} // namespace
+} // namespace ab
+
+using namespace ab;
+
+extern "C" {
+
+// ---- Gram -------------------------------------------------------------------------------------
+
+int ab_gram_sym_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, uint32_t flags,
+                  ab_matrix *out) {
+  AB_REQUIRE(h != nullptr && feats != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  DevProg P;
+  AB_TRY(compile_program(prog, nops, &P));
+  timings_reset(h);
+  phase_begin(h, PH_GRAM);
+  int s = gram_sym_device(h, P, feats, flags, out);
+  phase_end(h, PH_GRAM);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return s;
+}
+
+int ab_gram_cross_d(ab_handle h, const ab_op *prog, int nops, ab_matrix fx, ab_matrix fy,
+                    ab_matrix *out) {
+  AB_REQUIRE(h != nullptr && fx != nullptr && fy != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  DevProg P;
+  AB_TRY(compile_program(prog, nops, &P));
+  timings_reset(h);
+  phase_begin(h, PH_GRAM);
+  int s = gram_cross_device(h, P, fx, fy, out);
+  phase_end(h, PH_GRAM);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return s;
+}
+
+int ab_gram_sym(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+                uint32_t flags, ab_matrix *out) {
+  AB_REQUIRE(h != nullptr && out != nullptr && (feats != nullptr || n == 0) && n >= 0, "null");
+  Lock lock(h);
+  Scope sc(h);
+  ab_matrix_s *F = nullptr;
+  AB_TRY(upload_features(h, feats, n, dim, &F));
+  sc.own(F);
+  int s = ab_gram_sym_d(h, prog, nops, F, flags, out);
+  cudaStreamSynchronize(h->stream); // `feats` may be pageable: finish the copy before returning
+  return s;
+}
+
+int ab_gram_cross(ab_handle h, const ab_op *prog, int nops, const double *fx, int64_t n,
+                  const double *fy, int64_t m, int dim, ab_matrix *out) {
+  AB_REQUIRE(h != nullptr && out != nullptr && n >= 0 && m >= 0, "null");
+  Lock lock(h);
+  Scope sc(h);
+  ab_matrix_s *FX = nullptr, *FY = nullptr;
+  AB_TRY(upload_features(h, fx, n, dim, &FX));
+  sc.own(FX);
+  AB_TRY(upload_features(h, fy, m, dim, &FY));
+  sc.own(FY);
+  int s = ab_gram_cross_d(h, prog, nops, FX, FY, out);
+  cudaStreamSynchronize(h->stream);
+  return s;
+}
+
+int ab_gram_diag(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+                 double *out) {
+  AB_REQUIRE(h != nullptr && (out != nullptr || n == 0) && n >= 0, "null");
+  Lock lock(h);
+  Scope sc(h);
+  DevProg P;
+  AB_TRY(compile_program(prog, nops, &P));
+  ab_matrix_s *F = nullptr;
+  AB_TRY(upload_features(h, feats, n, dim, &F));
+  sc.own(F);
+  void *d = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(n < 1 ? 1 : n) * sizeof(double), &d));
+  AB_TRY(gram_diag_device(h, P, F, static_cast<double *>(d)));
+  return download_bytes(h, d, static_cast<size_t>(n) * sizeof(double), out);
+}
+
+int ab_matrix_add_diag(ab_handle h, ab_matrix m, const double *d) {
+  AB_REQUIRE(h != nullptr && m != nullptr && d != nullptr && m->rows == m->cols, "null/shape");
+  Lock lock(h);
+  Scope sc(h);
+  void *dd = nullptr;
+  AB_TRY(upload_bytes(h, sc, d, static_cast<size_t>(m->rows) * sizeof(double), &dd));
+  AB_TRY(add_diag(h, view(m), m->rows, static_cast<double *>(dd)));
+  AB_CUDA(cudaStreamSynchronize(h->stream));
+  return AB_OK;
+}
+
+// ---- factor -----------------------------------------------------------------------------------
+
+int ab_potrf(ab_handle h, ab_matrix m, ab_factor *out) {
+  AB_REQUIRE(h != nullptr && m != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  timings_reset(h);
+  phase_begin(h, PH_FACTOR);
+  int s = factorize(h, m, out);
+  phase_end(h, PH_FACTOR);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return s;
+}
+
+int ab_factor_free(ab_handle h, ab_factor f) {
+  AB_REQUIRE(h != nullptr, "null handle");
+  Lock lock(h);
+  delete_factor(h, f);
+  return AB_OK;
+}
+
+int ab_factor_rows(ab_factor f, int64_t *n) {
+  AB_REQUIRE(f != nullptr && n != nullptr, "null");
+  *n = f->n;
+  return AB_OK;
+}
+
+int ab_factor_info(ab_factor f, int64_t *first_bad_pivot) {
+  AB_REQUIRE(f != nullptr && first_bad_pivot != nullptr, "null");
+  *first_bad_pivot = f->bad_pivot;
+  return AB_OK;
+}
+
+static int solve_impl(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out,
+                      bool sqrt_only) {
+  AB_REQUIRE(h != nullptr && (rhs != nullptr || nrhs == 0) && (out != nullptr || nrhs == 0) &&
+                 nrhs >= 0,
+             "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  if (nrhs == 0 || f->n == 0) {
+    return AB_OK;
+  }
+  Scope sc(h);
+  timings_reset(h);
+  ab_matrix_s *X = nullptr;
+  phase_begin(h, PH_H2D);
+  AB_TRY(upload(h, rhs, f->n, nrhs, &X));
+  phase_end(h, PH_H2D);
+  sc.own(X);
+  phase_begin(h, PH_SOLVE);
+  AB_TRY(trsm_left_lower(h, view(f->m), f->dinv, f->n, view(X), nrhs));
+  if (!sqrt_only) {
+    AB_TRY(trsm_left_lower_T(h, view(f->m), f->dinv, f->n, view(X), nrhs));
+  }
+  phase_end(h, PH_SOLVE);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return download(h, X, 0, 0, f->n, nrhs, out);
+}
+
+int ab_factor_solve(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out) {
+  return solve_impl(h, f, rhs, nrhs, out, false);
+}
+
+int ab_factor_sqrt_solve(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out) {
+  return solve_impl(h, f, rhs, nrhs, out, true);
+}
+
+int ab_factor_logdet(ab_handle h, ab_factor f, double *out) {
+  AB_REQUIRE(h != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  if (f->n == 0) {
+    *out = 0.;
+    return AB_OK;
+  }
+  AB_TRY(logdet_chol(h, view(f->m), f->n, h->d_scalars));
+  AB_TRY(download_bytes(h, h->d_scalars, sizeof(double), h->h_scalars));
+  *out = h->h_scalars[0];
+  return AB_OK;
+}
+
+// nll from an existing factor and a device-resident deviation vector (n x 1 matrix).
+static int nll_device(ab_handle h, ab_factor f, ab_matrix_s *dev_copy, double *out) {
+  // quad = |L^-1 dev|^2 = dev^T K^-1 dev ; logdet = sum 2 log L_ii
+  phase_begin(h, PH_SOLVE);
+  AB_TRY(trsm_left_lower(h, view(f->m), f->dinv, f->n, view(dev_copy), 1));
+  phase_end(h, PH_SOLVE);
+  phase_begin(h, PH_REDUCE);
+  AB_TRY(dot(h, dev_copy->d, dev_copy->d, f->n, h->d_scalars + 1));
+  AB_TRY(logdet_chol(h, view(f->m), f->n, h->d_scalars));
+  phase_end(h, PH_REDUCE);
+  AB_TRY(download_bytes(h, h->d_scalars, 2 * sizeof(double), h->h_scalars));
+  const double log_det = h->h_scalars[0];
+  const double mahalanobis = h->h_scalars[1];
+  *out = 0.5 * (log_det + mahalanobis + static_cast<double>(f->n) * std::log(2 * M_PI));
+  return AB_OK;
+}
+
+int ab_factor_nll(ab_handle h, ab_factor f, const double *deviation, double *out) {
+  AB_REQUIRE(h != nullptr && deviation != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  Scope sc(h);
+  timings_reset(h);
+  ab_matrix_s *d = nullptr;
+  AB_TRY(upload(h, deviation, f->n, 1, &d));
+  sc.own(d);
+  int s = nll_device(h, f, d, out);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return s;
+}
+
+int ab_factor_inverse_diagonal(ab_handle h, ab_factor f, double *out) {
+  AB_REQUIRE(h != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  if (f->n == 0) {
+    return AB_OK;
+  }
+  Scope sc(h);
+  ab_matrix_s *W = nullptr;
+  AB_TRY(inverse_factor(h, sc, f, &W));
+  void *d = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(f->n) * sizeof(double), &d));
+  AB_TRY(column_dots(h, view(W), view(W), f->n, f->n, static_cast<double *>(d)));
+  return download_bytes(h, d, static_cast<size_t>(f->n) * sizeof(double), out);
+}
+
+// (K^-1)_gg = W[:, g]^T W[:, g] written to dA (k x k, leading dimension ldA); W = L^-1.
+static int inverse_block_device(ab_handle h, const ab_matrix_s *W, const int64_t *d_idx,
+                                const int64_t *h_idx, int64_t k, ab_matrix_s *G, MatView A) {
+  const int64_t n = W->rows;
+  int64_t row0 = n;
+  for (int64_t i = 0; i < k; ++i) {
+    AB_REQUIRE(h_idx[i] >= 0 && h_idx[i] < n, "group index out of range");
+    row0 = std::min(row0, h_idx[i]);
+  }
+  row0 = row0 / 2 * 2; // keep 16-byte alignment of the gathered panel rows
+  const int64_t rows = n - row0;
+  const dim3 grid(static_cast<unsigned>((rows + 255) / 256), static_cast<unsigned>(k));
+  gather_cols_kernel<<<grid, 256, 0, h->stream>>>(W->d, W->ld, row0, rows, d_idx, G->d, G->ld);
+  AB_LAUNCHED(h);
+  return gemm(h, GEMM_TRANS_A, k, k, rows, 1., view(G), view(G), 0., A);
+}
+
+int ab_factor_inverse_blocks(ab_handle h, ab_factor f, const int64_t *indices,
+                             const int64_t *offsets, int64_t ngroups, double *out) {
+  AB_REQUIRE(h != nullptr && indices != nullptr && offsets != nullptr && out != nullptr &&
+                 ngroups >= 0,
+             "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  if (ngroups == 0) {
+    return AB_OK;
+  }
+  Scope sc(h);
+  const int64_t total = offsets[ngroups];
+  int64_t maxg = 0;
+  for (int64_t g = 0; g < ngroups; ++g) {
+    maxg = std::max(maxg, offsets[g + 1] - offsets[g]);
+  }
+  ab_matrix_s *W = nullptr;
+  AB_TRY(inverse_factor(h, sc, f, &W));
+  void *d_idx = nullptr;
+  AB_TRY(upload_bytes(h, sc, indices, static_cast<size_t>(total) * sizeof(int64_t), &d_idx));
+  ab_matrix_s *G = nullptr, *A = nullptr;
+  AB_TRY(matrix_new(h, f->n, maxg, &G));
+  sc.own(G);
+  AB_TRY(matrix_new(h, maxg, maxg, &A));
+  sc.own(A);
+  double *cursor = out;
+  for (int64_t g = 0; g < ngroups; ++g) {
+    const int64_t k = offsets[g + 1] - offsets[g];
+    AB_TRY(inverse_block_device(h, W, static_cast<int64_t *>(d_idx) + offsets[g],
+                                indices + offsets[g], k, G, view(A)));
+    AB_TRY(download(h, A, 0, 0, k, k, cursor));
+    cursor += k * k;
+  }
+  return AB_OK;
+}
+
+__global__ void export_packed_kernel(const double *L, int64_t ld, int64_t n, double *out) {
+  // out(i,j) = L(i,j) / L(j,j) for i > j ; out(j,j) = L(j,j)^2 ; out(i,j) = L-like mirror for i < j
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= n) {
+    return;
+  }
+  const double ljj = L[j + j * ld];
+  if (i > j) {
+    out[i + j * n] = L[i + j * ld] / ljj;
+  } else if (i == j) {
+    out[i + j * n] = ljj * ljj;
+  } else {
+    out[i + j * n] = L[j + i * ld] / L[i + i * ld]; // symmetric fill, as Eigen's matrixLDLT is read via views
+  }
+}
+
+int ab_factor_export_packed(ab_handle h, ab_factor f, double *LD, int64_t *transpositions) {
+  AB_REQUIRE(h != nullptr && LD != nullptr, "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  const int64_t n = f->n;
+  if (n == 0) {
+    return AB_OK;
+  }
+  Scope sc(h);
+  void *d = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(n) * n * sizeof(double), &d));
+  for (int64_t c0 = 0; c0 < n; c0 += 65535) {
+    const int64_t nc = std::min<int64_t>(65535, n - c0);
+    AB_REQUIRE(c0 == 0, "export_packed supports n <= 65535");
+    const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(nc));
+    export_packed_kernel<<<grid, 256, 0, h->stream>>>(f->m->d, f->m->ld, n,
+                                                      static_cast<double *>(d));
+    AB_LAUNCHED(h);
+  }
+  AB_TRY(download_bytes(h, d, static_cast<size_t>(n) * n * sizeof(double), LD));
+  if (transpositions != nullptr) {
+    std::iota(transpositions, transpositions + n, int64_t(0));
+  }
+  return AB_OK;
+}
+
+// ---- exact GP ---------------------------------------------------------------------------------
+
+// K (+diag) -> factor.  feats: dim x n device matrix.  Consumes nothing; returns a new factor.
+static int build_and_factor(ab_handle h, const DevProg &P, const ab_matrix_s *feats,
+                            const double *d_yvar, ab_factor_s **out) {
+  ab_matrix_s *K = nullptr;
+  phase_begin(h, PH_GRAM);
+  AB_TRY(gram_sym_device(h, P, feats, AB_GRAM_LOWER_ONLY, &K));
+  if (d_yvar != nullptr) {
+    int s = add_diag(h, view(K), K->rows, d_yvar);
+    if (s != AB_OK) {
+      matrix_delete(h, K);
+      return s;
+    }
+  }
+  phase_end(h, PH_GRAM);
+  phase_begin(h, PH_FACTOR);
+  int s = factorize(h, K, out); // a NaN anywhere in K surfaces as a NaN pivot -> AB_ERR_NOT_PD
+  phase_end(h, PH_FACTOR);
+  return s;
+}
+
+int ab_gp_fit_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
+                ab_matrix yvar, ab_factor *factor, ab_matrix *information) {
+  AB_REQUIRE(h != nullptr && feats != nullptr && y != nullptr && factor != nullptr, "null");
+  AB_REQUIRE(y->rows == feats->cols && y->cols == 1, "targets shape");
+  AB_REQUIRE(yvar == nullptr || (yvar->rows == feats->cols && yvar->cols == 1), "variance shape");
+  Lock lock(h);
+  DevProg P;
+  AB_TRY(compile_program(prog, nops, &P));
+  timings_reset(h);
+  ab_factor_s *f = nullptr;
+  int s = build_and_factor(h, P, feats, yvar != nullptr ? yvar->d : nullptr, &f);
+  if (s != AB_OK) {
+    *factor = f; // non-null only for AB_ERR_NOT_PD
+    cudaEventRecord(h->ev_total_end, h->stream);
+    return s;
+  }
+  *factor = f;
+  if (information != nullptr) {
+    ab_matrix_s *x = nullptr;
+    AB_TRY(matrix_new(h, f->n, 1, &x));
+    phase_begin(h, PH_SOLVE);
+    cudaMemcpyAsync(x->d, y->d, static_cast<size_t>(f->n) * sizeof(double),
+                    cudaMemcpyDeviceToDevice, h->stream);
+    s = trsm_left_lower(h, view(f->m), f->dinv, f->n, view(x), 1);
+    if (s == AB_OK) {
+      s = trsm_left_lower_T(h, view(f->m), f->dinv, f->n, view(x), 1);
+    }
+    phase_end(h, PH_SOLVE);
+    if (s != AB_OK) {
+      matrix_delete(h, x);
+      return s;
+    }
+    *information = x;
+  }
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return AB_OK;
+}
+
+int ab_gp_fit(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+              const double *y, const double *yvar, ab_factor *factor, double *information) {
+  AB_REQUIRE(h != nullptr && factor != nullptr && n >= 0 && (n == 0 || (feats && y)), "null");
+  Lock lock(h);
+  Scope sc(h);
+  *factor = nullptr;
+  ab_matrix_s *F = nullptr, *Y = nullptr, *V = nullptr, *info = nullptr;
+  AB_TRY(upload_features(h, feats, n, dim, &F));
+  sc.own(F);
+  AB_TRY(upload(h, y, n, 1, &Y));
+  sc.own(Y);
+  if (yvar != nullptr) {
+    AB_TRY(upload(h, yvar, n, 1, &V));
+    sc.own(V);
+  }
+  int s = ab_gp_fit_d(h, prog, nops, F, Y, V, factor, information != nullptr ? &info : nullptr);
+  if (s != AB_OK) {
+    cudaStreamSynchronize(h->stream);
+    return s;
+  }
+  if (info != nullptr) {
+    sc.own(info);
+    AB_TRY(download(h, info, 0, 0, n, 1, information));
+  }
+  AB_CUDA(cudaStreamSynchronize(h->stream));
+  return AB_OK;
+}
+
+int ab_gp_nll_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
+                double *nll) {
+  AB_REQUIRE(h != nullptr && feats != nullptr && y != nullptr && nll != nullptr, "null");
+  AB_REQUIRE(y->rows == feats->cols && y->cols == 1, "targets shape");
+  Lock lock(h);
+  DevProg P;
+  AB_TRY(compile_program(prog, nops, &P));
+  Scope sc(h);
+  timings_reset(h);
+  const int64_t n = feats->cols;
+  if (n == 0) {
+    *nll = 0.;
+    return AB_OK;
+  }
+  ab_factor_s *f = nullptr;
+  int s = build_and_factor(h, P, feats, nullptr, &f);
+  if (s != AB_OK) {
+    delete_factor(h, f);
+    return s;
+  }
+  ab_matrix_s *d = nullptr;
+  s = matrix_new(h, n, 1, &d);
+  if (s == AB_OK) {
+    sc.own(d);
+    cudaMemcpyAsync(d->d, y->d, static_cast<size_t>(n) * sizeof(double), cudaMemcpyDeviceToDevice,
+                    h->stream);
+    s = nll_device(h, f, d, nll);
+  }
+  cudaEventRecord(h->ev_total_end, h->stream);
+  delete_factor(h, f);
+  return s;
+}
+
+int ab_gp_nll(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+              const double *y, double *nll) {
+  AB_REQUIRE(h != nullptr && nll != nullptr && n >= 0 && (n == 0 || (feats && y)), "null");
+  Lock lock(h);
+  Scope sc(h);
+  ab_matrix_s *F = nullptr, *Y = nullptr;
+  AB_TRY(upload_features(h, feats, n, dim, &F));
+  sc.own(F);
+  AB_TRY(upload(h, y, n, 1, &Y));
+  sc.own(Y);
+  int s = ab_gp_nll_d(h, prog, nops, F, Y, nll);
+  cudaStreamSynchronize(h->stream);
+  return s;
+}
+
+int ab_gp_fit_nll(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n,
+                  int dim, const double *y, ab_factor *factor, double *information, double *nll) {
+  AB_REQUIRE(h != nullptr && factor != nullptr && nll != nullptr, "null");
+  Lock lock(h);
+  AB_TRY(ab_gp_fit(h, prog, nops, feats, n, dim, y, nullptr, factor, information));
+  // dev^T K^-1 dev = y . information when information is available; use the factor directly.
+  return ab_factor_nll(h, *factor, y, nll);
+}
+
+int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const double *train_feats,
+                  int64_t n, int dim, const double *information, const double *test_feats,
+                  int64_t p, int what, double *mean, double *var, double *cov) {
+  AB_REQUIRE(h != nullptr && train_feats != nullptr && information != nullptr && p >= 0 &&
+                 (p == 0 || (test_feats != nullptr && mean != nullptr)),
+             "null");
+  AB_REQUIRE(what == AB_PREDICT_MEAN || (what == AB_PREDICT_MARGINAL && var != nullptr) ||
+                 (what == AB_PREDICT_JOINT && cov != nullptr),
+             "prediction kind / outputs");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  AB_REQUIRE(f->n == n, "factor size differs from training set");
+  if (p == 0) {
+    return AB_OK;
+  }
+  DevProg P;
+  AB_TRY(compile_program(prog, nops, &P));
+  Scope sc(h);
+  timings_reset(h);
+  ab_matrix_s *FX = nullptr, *FT = nullptr, *info = nullptr, *cross = nullptr, *m = nullptr;
+  phase_begin(h, PH_H2D);
+  AB_TRY(upload_features(h, train_feats, n, dim, &FX));
+  sc.own(FX);
+  AB_TRY(upload_features(h, test_feats, p, dim, &FT));
+  sc.own(FT);
+  AB_TRY(upload(h, information, n, 1, &info));
+  sc.own(info);
+  phase_end(h, PH_H2D);
+  phase_begin(h, PH_PREDICT);
+  // cross_cov = K(train, test), n x p  (gp.hpp:317-318)
+  AB_TRY(gram_cross_device(h, P, FX, FT, &cross));
+  sc.own(cross);
+  // mean = cross^T information  (gp.hpp:82-85)
+  AB_TRY(matrix_new(h, p, 1, &m));
+  sc.own(m);
+  AB_TRY(gemm(h, GEMM_TRANS_A, p, 1, n, 1., view(cross), view(info), 0., view(m)));
+  if (what == AB_PREDICT_MARGINAL) {
+    // var = k(x*,x*) - colsum((L^-1 cross)^2)  (gp.hpp:87-101)
+    void *d_prior = nullptr, *d_expl = nullptr;
+    AB_TRY(sc.alloc(static_cast<size_t>(p) * sizeof(double), &d_prior));
+    AB_TRY(sc.alloc(static_cast<size_t>(p) * sizeof(double), &d_expl));
+    AB_TRY(gram_diag_device(h, P, FT, static_cast<double *>(d_prior)));
+    AB_TRY(trsm_left_lower(h, view(f->m), f->dinv, n, view(cross), p));
+    AB_TRY(column_dots(h, view(cross), view(cross), n, p, static_cast<double *>(d_expl)));
+    phase_end(h, PH_PREDICT);
+    std::vector<double> prior(p), expl(p);
+    AB_TRY(download_bytes(h, d_prior, static_cast<size_t>(p) * sizeof(double), prior.data()));
+    AB_TRY(download_bytes(h, d_expl, static_cast<size_t>(p) * sizeof(double), expl.data()));
+    for (int64_t i = 0; i < p; ++i) {
+      var[i] = prior[i] - expl[i];
+    }
+  } else if (what == AB_PREDICT_JOINT) {
+    // cov = K(test,test) - (L^-1 cross)^T (L^-1 cross)  (gp.hpp:103-113)
+    ab_matrix_s *prior = nullptr;
+    AB_TRY(gram_sym_device(h, P, FT, AB_GRAM_FULL, &prior));
+    sc.own(prior);
+    AB_TRY(trsm_left_lower(h, view(f->m), f->dinv, n, view(cross), p));
+    AB_TRY(gemm(h, GEMM_TRANS_A, p, p, n, -1., view(cross), view(cross), 1., view(prior)));
+    phase_end(h, PH_PREDICT);
+    AB_TRY(download(h, prior, 0, 0, p, p, cov));
+  } else {
+    phase_end(h, PH_PREDICT);
+  }
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return download(h, m, 0, 0, p, 1, mean);
+}
+
+int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *information,
+             const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+             double *mean, double *var, double *joint, double *score) {
+  AB_REQUIRE(h != nullptr && y != nullptr && information != nullptr && indices != nullptr &&
+                 offsets != nullptr && mean != nullptr && ngroups >= 0,
+             "null");
+  AB_REQUIRE(what == AB_PREDICT_MEAN || (what == AB_PREDICT_MARGINAL && var != nullptr) ||
+                 (what == AB_PREDICT_JOINT && joint != nullptr),
+             "prediction kind / outputs");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  const int64_t n = f->n;
+  if (ngroups == 0 || n == 0) {
+    if (score != nullptr) {
+      *score = 0.;
+    }
+    return AB_OK;
+  }
+  const int64_t total = offsets[ngroups];
+  AB_REQUIRE(total <= n, "more held-out indices than observations");
+  int64_t maxg = 0;
+  for (int64_t g = 0; g < ngroups; ++g) {
+    AB_REQUIRE(offsets[g + 1] >= offsets[g], "offsets must be non-decreasing");
+    maxg = std::max(maxg, offsets[g + 1] - offsets[g]);
+  }
+  Scope sc(h);
+  timings_reset(h);
+  ab_matrix_s *W = nullptr;
+  phase_begin(h, PH_SOLVE);
+  AB_TRY(inverse_factor(h, sc, f, &W));
+  phase_end(h, PH_SOLVE);
+
+  void *d_y = nullptr, *d_info = nullptr, *d_idx = nullptr, *d_mean = nullptr, *d_var = nullptr;
+  AB_TRY(upload_bytes(h, sc, y, static_cast<size_t>(n) * sizeof(double), &d_y));
+  AB_TRY(upload_bytes(h, sc, information, static_cast<size_t>(n) * sizeof(double), &d_info));
+  AB_TRY(upload_bytes(h, sc, indices, static_cast<size_t>(total) * sizeof(int64_t), &d_idx));
+  AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_mean));
+  AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_var));
+  AB_CUDA(cudaMemsetAsync(d_mean, 0, static_cast<size_t>(n) * sizeof(double), h->stream));
+  AB_CUDA(cudaMemsetAsync(d_var, 0, static_cast<size_t>(n) * sizeof(double), h->stream));
+
+  phase_begin(h, PH_PREDICT);
+  double total_score = 0.;
+  if (maxg == 1 && total == n && ngroups == n) {
+    // pure leave-one-out: everything is element-wise on diag(K^-1)
+    void *d_a = nullptr, *d_terms = nullptr;
+    AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_a));
+    AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_terms));
+    AB_TRY(column_dots(h, view(W), view(W), n, n, static_cast<double *>(d_a)));
+    loo_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, h->stream>>>(
+        static_cast<double *>(d_a), static_cast<double *>(d_y), static_cast<double *>(d_info), n,
+        static_cast<double *>(d_mean), static_cast<double *>(d_var),
+        static_cast<double *>(d_terms));
+    AB_LAUNCHED(h);
+    phase_end(h, PH_PREDICT);
+    AB_TRY(download_bytes(h, d_mean, static_cast<size_t>(n) * sizeof(double), mean));
+    if (what != AB_PREDICT_MEAN) {
+      // for 1x1 groups the joint blocks, in key order, are the variances in index order
+      std::vector<double> v(n);
+      AB_TRY(download_bytes(h, d_var, static_cast<size_t>(n) * sizeof(double), v.data()));
+      if (what == AB_PREDICT_MARGINAL) {
+        std::copy(v.begin(), v.end(), var);
+      } else {
+        for (int64_t g = 0; g < n; ++g) {
+          joint[g] = v[indices[offsets[g]]];
+        }
+      }
+    }
+    if (score != nullptr) {
+      std::vector<double> t(n);
+      AB_TRY(download_bytes(h, d_terms, static_cast<size_t>(n) * sizeof(double), t.data()));
+      for (int64_t g = 0; g < n; ++g) {
+        total_score += t[indices[offsets[g]]];
+      }
+      *score = total_score;
+    }
+    cudaEventRecord(h->ev_total_end, h->stream);
+    return AB_OK;
+  }
+
+  // general groups: A_g = (K^-1)_gg ; x = A_g^-1 v_g ; mean_g = y_g - x ; cov_g = A_g^-1
+  ab_matrix_s *G = nullptr, *A = nullptr, *Wg = nullptr, *Tg = nullptr, *x = nullptr;
+  AB_TRY(matrix_new(h, n, maxg, &G));
+  sc.own(G);
+  AB_TRY(matrix_new(h, maxg, maxg, &A));
+  sc.own(A);
+  AB_TRY(matrix_new(h, maxg, maxg, &Wg));
+  sc.own(Wg);
+  const int64_t half = round_up((maxg + 1) / 2, LEAF) + LEAF;
+  AB_TRY(matrix_new(h, half, half, &Tg));
+  sc.own(Tg);
+  AB_TRY(matrix_new(h, maxg, 2, &x));
+  sc.own(x);
+  void *d_diag = nullptr, *d_gscal = nullptr, *d_joint = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(maxg) * sizeof(double), &d_diag));
+  AB_TRY(sc.alloc(static_cast<size_t>(ngroups) * 2 * sizeof(double), &d_gscal));
+  ab_matrix_s *Cg = nullptr;
+  if (what == AB_PREDICT_JOINT) {
+    AB_TRY(matrix_new(h, maxg, maxg, &Cg));
+    sc.own(Cg);
+  }
+  (void)d_joint;
+  const int64_t nleaf = (maxg + LEAF - 1) / LEAF;
+  void *d_ginv = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(nleaf) * LEAF * LEAF * sizeof(double), &d_ginv));
+  double *joint_cursor = joint;
+  h->h_flags[0] = INT_MAX;
+  AB_CUDA(cudaMemcpyAsync(h->d_flags, h->h_flags, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  for (int64_t g = 0; g < ngroups; ++g) {
+    const int64_t k = offsets[g + 1] - offsets[g];
+    if (k == 0) {
+      continue;
+    }
+    const int64_t *gi = static_cast<int64_t *>(d_idx) + offsets[g];
+    AB_TRY(inverse_block_device(h, W, gi, indices + offsets[g], k, G, view(A)));
+    AB_TRY(potrf(h, view(A), k, static_cast<double *>(d_ginv), h->d_flags));
+    // x = A^-1 v_g  (column 0 of x), keep v_g in column 1 for the score
+    gather_vec_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, h->stream>>>(
+        static_cast<double *>(d_info), gi, k, x->d);
+    AB_LAUNCHED(h);
+    AB_CUDA(cudaMemcpyAsync(x->d + x->ld, x->d, static_cast<size_t>(k) * sizeof(double),
+                            cudaMemcpyDeviceToDevice, h->stream));
+    AB_TRY(trsm_left_lower(h, view(A), static_cast<double *>(d_ginv), k, view(x), 1));
+    AB_TRY(trsm_left_lower_T(h, view(A), static_cast<double *>(d_ginv), k, view(x), 1));
+    double *diag = nullptr;
+    if (what != AB_PREDICT_MEAN) {
+      // A^-1 = Wg^T Wg with Wg = chol(A)^-1
+      AB_TRY(fill(h, view(Wg), k, k, 0.));
+      AB_TRY(trtri_rec(h, view(A), static_cast<double *>(d_ginv), k, view(Wg), view(Tg)));
+      if (what == AB_PREDICT_MARGINAL) {
+        AB_TRY(column_dots(h, view(Wg), view(Wg), k, k, static_cast<double *>(d_diag)));
+        diag = static_cast<double *>(d_diag);
+      } else {
+        AB_TRY(gemm(h, GEMM_TRANS_A, k, k, k, 1., view(Wg), view(Wg), 0., view(Cg)));
+      }
+    }
+    heldout_scatter_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, h->stream>>>(
+        static_cast<double *>(d_y), x->d, diag, gi, k, static_cast<double *>(d_mean),
+        diag != nullptr ? static_cast<double *>(d_var) : nullptr);
+    AB_LAUNCHED(h);
+    if (score != nullptr) {
+      // NLL(dev = x, cov = A^-1) = 0.5 (-logdet(A) + x^T A x + k log 2pi), x^T A x = x . v_g
+      AB_TRY(logdet_chol(h, view(A), k, static_cast<double *>(d_gscal) + 2 * g));
+      AB_TRY(dot(h, x->d, x->d + x->ld, k, static_cast<double *>(d_gscal) + 2 * g + 1));
+    }
+    if (what == AB_PREDICT_JOINT) {
+      AB_TRY(download(h, Cg, 0, 0, k, k, joint_cursor));
+      joint_cursor += k * k;
+    }
+  }
+  phase_end(h, PH_PREDICT);
+  AB_TRY(download_bytes(h, d_mean, static_cast<size_t>(n) * sizeof(double), mean));
+  if (what == AB_PREDICT_MARGINAL) {
+    AB_TRY(download_bytes(h, d_var, static_cast<size_t>(n) * sizeof(double), var));
+  }
+  AB_TRY(download_bytes(h, h->d_flags, sizeof(int), h->h_flags));
+  if (h->h_flags[0] != INT_MAX) {
+    set_error("a held-out block of the inverse covariance is not positive definite");
+    return AB_ERR_NOT_PD;
+  }
+  if (score != nullptr) {
+    std::vector<double> gs(static_cast<size_t>(ngroups) * 2);
+    AB_TRY(download_bytes(h, d_gscal, gs.size() * sizeof(double), gs.data()));
+    for (int64_t g = 0; g < ngroups; ++g) {
+      const int64_t k = offsets[g + 1] - offsets[g];
+      if (k == 0) {
+        continue;
+      }
+      total_score += 0.5 * (-gs[2 * g] + gs[2 * g + 1] + static_cast<double>(k) * std::log(2 * M_PI));
+    }
+    *score = total_score;
+  }
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return AB_OK;
+}
+
+// ---- integer contract -------------------------------------------------------------------------
+
+int ab_group_indexers(const int64_t *item_keys, int64_t n, int64_t *keys, int64_t *offsets,
+                      int64_t *indices, int64_t *ngroups) {
+  AB_REQUIRE(n >= 0 && offsets != nullptr && ngroups != nullptr &&
+                 (n == 0 || (item_keys && keys && indices)),
+             "null");
+  // std::map<Key, std::vector<size_t>> semantics (group_by.hpp:349-376): keys ascending, members in
+  // encounter order == ascending index.  A stable sort of indices by key reproduces it exactly.
+  std::vector<int64_t> order(static_cast<size_t>(n));
+  std::iota(order.begin(), order.end(), int64_t(0));
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int64_t a, int64_t b) { return item_keys[a] < item_keys[b]; });
+  int64_t g = 0;
+  offsets[0] = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t key = item_keys[order[static_cast<size_t>(i)]];
+    if (i == 0 || key != keys[g - 1]) {
+      if (i > 0) {
+        offsets[g] = i;
+      }
+      keys[g++] = key;
+    }
+    indices[i] = order[static_cast<size_t>(i)];
+  }
+  offsets[g] = n;
+  *ngroups = g;
+  return AB_OK;
+}
+
+} // extern "C"

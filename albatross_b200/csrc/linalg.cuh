@@ -1,0 +1,55 @@
+// Dense fp64 building blocks on the device: DMMA GEMM family, blocked Cholesky, triangular solves,
+// reductions.  All matrices column-major.
+#pragma once
+
+#include "common.cuh"
+
+namespace ab {
+
+constexpr int LEAF = 64; // diagonal-block size of the recursive factorisation / solves
+
+struct MatView {
+  double *p;
+  int64_t ld;
+  __host__ __device__ MatView sub(int64_t r, int64_t c) const { return MatView{p + r + c * ld, ld}; }
+};
+
+enum GemmFlags : unsigned {
+  GEMM_TRANS_A = 1u, // op(A) = A^T, A stored k x m
+  GEMM_TRANS_B = 2u, // op(B) = B^T, B stored n x k
+  GEMM_LOWER = 4u    // C is square (m == n): only tiles touching the lower triangle are computed
+};
+
+// C[m x n] = alpha * op(A) * op(B) + beta * C.   beta == 0 never reads C.
+// In-place use (C aliasing A or B) is allowed only when one CTA owns the whole aliased extent:
+// C == A with n <= 128 and k == n (right-multiplication by a small matrix), or C == B with
+// m <= 128 and k == m (left-multiplication).
+int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double alpha, MatView A,
+         MatView B, double beta, MatView C);
+
+// Blocked Cholesky of the lower triangle of the n x n matrix A, in place.  dinv receives the
+// explicit inverses of the LEAF x LEAF diagonal blocks of L (block j at dinv + j*LEAF*LEAF,
+// column-major LEAF x LEAF, upper triangle zero).  d_bad: device int, atomicMin'ed with the global
+// index of the first non-positive pivot (initialise to INT_MAX).
+int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad);
+
+// X <- L^-1 X  (n x p), X <- L^-T X, X <- X L^-T (m x n, L n x n), using dinv for the leaves.
+int trsm_left_lower(ab_handle_s *h, MatView L, const double *dinv, int64_t n, MatView X, int64_t p);
+int trsm_left_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, MatView X,
+                      int64_t p);
+int trsm_right_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, MatView X,
+                       int64_t m);
+
+// out[0] = sum_i 2 log(L_ii)
+int logdet_chol(ab_handle_s *h, MatView L, int64_t n, double *d_out);
+// out[0] = sum_i a_i * b_i
+int dot(ab_handle_s *h, const double *a, const double *b, int64_t n, double *d_out);
+// out[j] = sum_i A(i,j) * B(i,j), j < cols
+int column_dots(ab_handle_s *h, MatView A, MatView B, int64_t rows, int64_t cols, double *d_out);
+int add_diag(ab_handle_s *h, MatView A, int64_t n, const double *d_diag);
+int fill(ab_handle_s *h, MatView A, int64_t rows, int64_t cols, double value);
+int set_identity(ab_handle_s *h, MatView A, int64_t n);
+// NaN scan of the lower triangle (gp.hpp:66): sets *d_flag = 1 if any NaN.
+int has_nan_lower(ab_handle_s *h, MatView A, int64_t n, int *d_flag);
+
+} // namespace ab

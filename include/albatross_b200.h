@@ -1,0 +1,262 @@
+/*
+ * albatross_b200 — C ABI of the B200-native exact-GP hot path.
+ *
+ * This is the drop-in boundary.  The reference (swift-nav/albatross) has no FFI:
+ * its "operator API" is a set of C++ template concepts.  The C++ trait layer shipped in
+ * albatross_b200/include/albatross/ re-creates those concepts (same names and signatures) and calls
+ * ONLY the functions below; INTEGRATION.md shows the binding a reference maintainer would add.
+ * Each entry point cites the reference routine it replaces; paths are relative to the reference
+ * root, `src/` = include/albatross/src/.
+ *
+ * Conventions
+ *   - plain C types only; all sizes int64_t; matrices column-major fp64 (Eigen::MatrixXd layout);
+ *   - features are AoS doubles, point i at feats[i*dim .. i*dim+dim) (std::vector<double> for dim 1,
+ *     std::vector<Eigen::Matrix<double,dim,1>> otherwise) — equivalently a dim x n col-major matrix;
+ *   - `const double *` / `double *` arguments are HOST pointers; device-resident data only ever
+ *     appears behind the opaque ab_matrix / ab_factor handles;
+ *   - every function returns an ab_status (0 = ok); ab_last_error() describes the last failure on the
+ *     calling thread.  The reference itself has no error channel (ALBATROSS_ASSERT,
+ *     src/details/error_handling.hpp:37-45); the C++ layer asserts on non-zero;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     AB_ERR_CUDA.
+ *   - a handle is bound to one GPU and one stream (one process per GPU); calls on one handle are
+ *     serialised by an internal mutex, so concurrent tuner threads may share it.
+ */
+#ifndef ALBATROSS_B200_H
+#define ALBATROSS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB_VERSION 1
+
+#if defined(__GNUC__)
+#define AB_API __attribute__((visibility("default")))
+#else
+#define AB_API
+#endif
+
+typedef enum {
+  AB_OK = 0,
+  AB_ERR_INVALID = 1,      /* bad argument / malformed covariance program */
+  AB_ERR_CUDA = 2,         /* CUDA runtime error or no device */
+  AB_ERR_ALLOC = 3,        /* device or host allocation failed */
+  AB_ERR_NOT_PD = 4,       /* non-positive pivot met in the factorisation (see ab_factor_info) */
+  AB_ERR_NCCL = 5,         /* collective failed */
+  AB_ERR_UNSUPPORTED = 6   /* feature/covariance type without a device form */
+} ab_status;
+
+/*
+ * Covariance program: the compile-time Sum/Product tree of the reference
+ * (src/covariance_functions/covariance_function.hpp:222-420) flattened to postfix by the C++ trait
+ * layer at every call (hyper-parameters are re-read live, SURVEY.md §5 "Config").
+ * Leaves push k(x,y); AB_OP_SUM / AB_OP_PRODUCT pop rhs then lhs and push the combination.
+ */
+typedef enum {
+  AB_OP_SQUARED_EXPONENTIAL = 1, /* p0 = length_scale, p1 = sigma   src/covariance_functions/radial.hpp:25-33   */
+  AB_OP_EXPONENTIAL = 2,         /* p0 = length_scale, p1 = sigma   radial.hpp:191-198 */
+  AB_OP_MATERN32 = 3,            /* p0 = length_scale, p1 = sigma   radial.hpp:289-297 */
+  AB_OP_MATERN52 = 4,            /* p0 = length_scale, p1 = sigma   radial.hpp:461-470 */
+  AB_OP_CONSTANT = 5,            /* p0 = sigma                      src/covariance_functions/polynomials.hpp:56-60 */
+  AB_OP_INDEPENDENT_NOISE = 6,   /* p0 = sigma; value equality      src/covariance_functions/noise.hpp:37-43 */
+  AB_OP_SUM = 7,                 /* lhs + rhs                       covariance_function.hpp:270-272 */
+  AB_OP_PRODUCT = 8              /* lhs != 0 ? lhs * rhs : lhs      covariance_function.hpp:361-367 */
+} ab_opcode;
+
+typedef struct {
+  int32_t op; /* ab_opcode */
+  int32_t reserved;
+  double p0;
+  double p1;
+} ab_op;
+
+#define AB_MAX_OPS 32
+#define AB_MAX_DIM 8
+
+typedef struct ab_handle_s *ab_handle;
+typedef struct ab_matrix_s *ab_matrix; /* device-resident column-major fp64 matrix */
+typedef struct ab_factor_s *ab_factor; /* device-resident factor K = L L^T (D = diag(L)^2, P = I) */
+
+/* Per-phase device times of the most recent GP-level call, CUDA events, milliseconds. */
+typedef struct {
+  double h2d_ms;
+  double gram_ms;
+  double factor_ms;
+  double solve_ms;
+  double reduce_ms;
+  double predict_ms;
+  double d2h_ms;
+  double total_ms;
+  int64_t kernel_launches; /* kernels launched by this library since ab_create / last reset */
+} ab_phase_times;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+
+/* Binds a handle to CUDA device `device` with its own non-blocking stream. */
+AB_API int ab_create(ab_handle *out, int device);
+/* Same, but work is enqueued on the caller's stream (a cudaStream_t passed as void*). */
+AB_API int ab_create_on_stream(ab_handle *out, int device, void *cuda_stream);
+AB_API int ab_destroy(ab_handle h);
+AB_API const char *ab_last_error(void);
+AB_API int ab_version(void);
+AB_API int ab_device_count(int *count);
+AB_API int ab_synchronize(ab_handle h);
+AB_API int ab_timings(ab_handle h, ab_phase_times *out);
+AB_API int ab_reset_counters(ab_handle h);
+/* Releases the handle's cached device workspace (buffers are otherwise recycled between calls). */
+AB_API int ab_trim(ab_handle h);
+
+/* ---- device matrices ----------------------------------------------------------------------- */
+
+AB_API int ab_matrix_upload(ab_handle h, const double *host, int64_t rows, int64_t cols, ab_matrix *out);
+AB_API int ab_matrix_alloc(ab_handle h, int64_t rows, int64_t cols, ab_matrix *out);
+AB_API int ab_matrix_download(ab_handle h, ab_matrix m, double *host);
+/* Copies the rows x cols block starting at (row0, col0) into `host` (column-major, ld = rows). */
+AB_API int ab_matrix_download_block(ab_handle h, ab_matrix m, int64_t row0, int64_t col0, int64_t rows,
+                             int64_t cols, double *host);
+AB_API int ab_matrix_dims(ab_matrix m, int64_t *rows, int64_t *cols);
+AB_API int ab_matrix_free(ab_handle h, ab_matrix m);
+/* Raw device pointer + leading dimension, for callers that own CUDA code themselves. */
+AB_API int ab_matrix_device_ptr(ab_matrix m, void **ptr, int64_t *ld);
+/* K(i,i) += d[i]: `cov += targets.covariance` of src/models/gp.hpp:65. */
+AB_API int ab_matrix_add_diag(ab_handle h, ab_matrix m, const double *d);
+
+/* ---- Gram construction --------------------------------------------------------------------- */
+
+#define AB_GRAM_FULL 0u        /* full symmetric n x n (what the reference returns) */
+#define AB_GRAM_LOWER_ONLY 1u  /* only i >= j is written (enough for ab_potrf) */
+
+/*
+ * Symmetric Gram K_ij = k(x_i, x_j).
+ * Replaces CovarianceFunction::operator()(const std::vector<X>&, ThreadPool*)
+ * src/covariance_functions/covariance_function.hpp:128-137 -> compute_covariance_matrix
+ * src/covariance_functions/callers.hpp:107-166.
+ */
+AB_API int ab_gram_sym(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+                uint32_t flags, ab_matrix *out);
+/*
+ * Cross Gram C_ij = k(x_i, y_j), n x m.
+ * Replaces operator()(const std::vector<X>&, const std::vector<Y>&, ThreadPool*)
+ * covariance_function.hpp:142-151 -> callers.hpp:38-102.
+ */
+AB_API int ab_gram_cross(ab_handle h, const ab_op *prog, int nops, const double *fx, int64_t n,
+                  const double *fy, int64_t m, int dim, ab_matrix *out);
+/*
+ * k(x_i, x_i) -> out[n] (host).  Replaces CovarianceFunction::diagonal
+ * covariance_function.hpp:156-168 and the prior-variance loop src/models/gp.hpp:339-343.
+ */
+AB_API int ab_gram_diag(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+                 double *out);
+/* Device-resident variants: feats is a dim x n ab_matrix; used when inputs already live in HBM. */
+AB_API int ab_gram_sym_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, uint32_t flags,
+                  ab_matrix *out);
+AB_API int ab_gram_cross_d(ab_handle h, const ab_op *prog, int nops, ab_matrix fx, ab_matrix fy,
+                    ab_matrix *out);
+
+/* ---- factorisation (the CovarianceRepresentation concept, src/models/gp.hpp:42-45) ---------- */
+
+/*
+ * In-place blocked Cholesky of the lower triangle of `m`; `m` is consumed (owned by the factor).
+ * Replaces Eigen::SerializableLDLT(const MatrixXd&) src/eigen/serializable_ldlt.hpp:27 ->
+ * LDLT::compute third_party/eigen/Eigen/src/Cholesky/LDLT.h:488-521.  The device factor is
+ * unpivoted (P = I, D = diag(L)^2); results agree with the pivoted reference to rounding.
+ * Returns AB_ERR_NOT_PD if a pivot <= 0 (or NaN) is met; the factor is still returned so that
+ * ab_factor_info can report the offending index, but must not be used for solves.
+ */
+AB_API int ab_potrf(ab_handle h, ab_matrix m, ab_factor *out);
+AB_API int ab_factor_free(ab_handle h, ab_factor f);
+AB_API int ab_factor_rows(ab_factor f, int64_t *n);
+/* first_bad_pivot = -1 when the matrix was positive definite (is_positive_definite(), :36). */
+AB_API int ab_factor_info(ab_factor f, int64_t *first_bad_pivot);
+/* out = K^-1 rhs, n x nrhs.  LDLT::solve, LDLT.h:558-592. */
+AB_API int ab_factor_solve(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out);
+/* out = D^-1/2 L^-1 P rhs = L_chol^-1 rhs.  SerializableLDLT::sqrt_solve, serializable_ldlt.hpp:100-109. */
+AB_API int ab_factor_sqrt_solve(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out);
+/* sum log D_ii.  serializable_ldlt.hpp:128-135. */
+AB_API int ab_factor_logdet(ab_handle h, ab_factor f, double *out);
+/* 0.5 (log|K| + dev^T K^-1 dev + n log 2pi).  src/evaluation/likelihood.hpp:38-47. */
+AB_API int ab_factor_nll(ab_handle h, ab_factor f, const double *deviation, double *out);
+/* diag(K^-1).  serializable_ldlt.hpp:181-199. */
+AB_API int ab_factor_inverse_diagonal(ab_handle h, ab_factor f, double *out);
+/*
+ * (K^-1)_gg for each group g = indices[offsets[g] .. offsets[g+1]); blocks written back to back,
+ * column-major each.  serializable_ldlt.hpp:137-175.
+ */
+AB_API int ab_factor_inverse_blocks(ab_handle h, ab_factor f, const int64_t *indices,
+                             const int64_t *offsets, int64_t ngroups, double *out);
+/*
+ * Materialises the factor in Eigen::SerializableLDLT's packed layout: strict lower = unit L,
+ * diagonal = D, transpositions = identity (src/cereal/serializable_ldlt.hpp:18-32).
+ */
+AB_API int ab_factor_export_packed(ab_handle h, ab_factor f, double *LD, int64_t *transpositions);
+
+/* ---- exact GP (src/models/gp.hpp) ---------------------------------------------------------- */
+
+/*
+ * model.fit(dataset): K = k(X,X) (+ diag(yvar) when yvar != NULL), factor, information = K^-1 y.
+ * Replaces GaussianProcessBase::_fit_impl gp.hpp:285-294 + Fit<GPFit<...>> ctor gp.hpp:61-69.
+ * `y` must already have the mean function removed by the caller (ZeroMean: unchanged).
+ * information may be NULL.  A NaN in K yields AB_ERR_NOT_PD (ALBATROSS_ASSERT(!cov.hasNaN())).
+ */
+AB_API int ab_gp_fit(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+              const double *y, const double *yvar, ab_factor *factor, double *information);
+/*
+ * Data term of -model.log_likelihood(dataset): builds and factors K afresh, exactly like
+ * gp.hpp:443-451 -> likelihood.hpp:53-67 (no targets.covariance).  The prior term is a host scalar
+ * added by the caller.
+ */
+AB_API int ab_gp_nll(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+              const double *y, double *nll);
+/*
+ * fit + nll sharing ONE Gram build and ONE factorisation (valid when yvar == NULL, where the two
+ * reference matrices coincide).  Offered for tuner loops; not what model.fit + log_likelihood do.
+ */
+AB_API int ab_gp_fit_nll(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n,
+                  int dim, const double *y, ab_factor *factor, double *information, double *nll);
+
+#define AB_PREDICT_MEAN 0
+#define AB_PREDICT_MARGINAL 1
+#define AB_PREDICT_JOINT 2
+/*
+ * fit_model.predict(test).{mean,marginal,joint}().  Replaces _predict_impl x3 gp.hpp:313-366 and
+ * gp_{mean,marginal,joint}_prediction gp.hpp:82-113.  mean: p; var: p (marginal); cov: p*p (joint).
+ */
+AB_API int ab_gp_predict(ab_handle h, ab_factor factor, const ab_op *prog, int nops,
+                  const double *train_feats, int64_t n, int dim, const double *information,
+                  const double *test_feats, int64_t p, int what, double *mean, double *var,
+                  double *cov);
+/*
+ * Leave-one-group-out predictions from an existing fit.  Replaces
+ * details::held_out_predictions src/evaluation/cross_validation_utils.hpp:199-232 ->
+ * held_out_prediction :172-197, scattered back by index (concatenate_*_predictions :59-100).
+ * groups: CSR (indices, offsets, ngroups) exactly as GroupIndexer iterates (std::map key order).
+ * what = MEAN: mean[n]; MARGINAL: mean[n], var[n]; JOINT: mean[n], joint = A_g^-1 blocks back to
+ * back.  score (optional) = sum_g NLL(joint_g, truth_g) (model_metrics.hpp:59-90, data term).
+ */
+AB_API int ab_gp_cv(ab_handle h, ab_factor factor, const double *y, const double *information,
+             const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+             double *mean, double *var, double *joint, double *score);
+
+/* Device-resident variants (inputs already in HBM; results stay in HBM unless a host ptr is given). */
+AB_API int ab_gp_fit_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
+                ab_matrix yvar, ab_factor *factor, ab_matrix *information);
+AB_API int ab_gp_nll_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
+                double *nll);
+
+/* ---- integer contract helpers (host; bit-exact with src/indexing/) -------------------------- */
+
+/*
+ * group_by(...).indexers() given one integer key per item: keys ascending, member indices in
+ * encounter order (IndexerBuilder::build src/indexing/group_by.hpp:349-376).  Returns ngroups
+ * through *ngroups.  keys/offsets/indices must hold n, n+1, n entries.
+ */
+AB_API int ab_group_indexers(const int64_t *item_keys, int64_t n, int64_t *keys, int64_t *offsets,
+                      int64_t *indices, int64_t *ngroups);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALBATROSS_B200_H */

@@ -1,0 +1,219 @@
+"""GPU parity: factorisation, solves, reductions, exact-GP fit / predict / NLL / cross-validation
+through the C ABI vs the oracle.  Tolerance: 1e-9 relative (BASELINE.json north_star) unless a
+tighter one is written; index outputs are bit-exact."""
+import numpy as np
+import pytest
+
+from albatross_b200 import capi
+from albatross_b200.capi import JOINT, MARGINAL, MEAN
+from oracle.oracle import Ref, Restate, group_keys
+from tests.helpers import GP_COVS, PARAMS, assert_close, features, prog, rel_err, targets
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def spd(n, seed, dim=3, cid=8):
+    ops, pp = prog(cid)
+    return Restate.gram_sym(ops, pp, features(n, dim, seed))
+
+
+# ---- SerializableLDLT surface (tests/test_serializable_ldlt.cc:34-85) ---------------------------
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 129, 200, 333, 1000])
+def test_factor_solve_logdet(handle, n):
+    A = spd(n, seed=n)
+    rhs = np.random.default_rng(n).standard_normal((n, 3))
+    f = handle.potrf(handle.upload(A))
+    assert f.is_positive_definite() and f.n == n
+    want = Restate.ldlt(A, rhs=rhs)
+    assert_close(f.solve(rhs), want["solve"], RTOL, f"solve n={n}")
+    assert_close(f.solve(rhs[:, 0]), want["solve"][:, 0], RTOL)
+    assert abs(f.log_determinant() - want["logdet"]) <= RTOL * max(1.0, abs(want["logdet"]))
+    # sqrt_solve is representation dependent (pivoting); its Gram is not:
+    s = f.sqrt_solve(rhs)
+    assert_close(s.T @ s, rhs.T @ want["solve"], RTOL, "sqrt_solve identity")
+    # L L^T reproduces A
+    LD, tr = f.export_packed()
+    assert np.array_equal(tr, np.arange(n))
+    L = np.tril(LD, -1) + np.eye(n)
+    assert_close((L * np.diag(LD)) @ L.T, A, 1e-12, "L D L^T")
+
+
+def test_ldlt_wrapper_fixture(handle, golden):
+    _, ref = golden
+    A, rhs = ref["ldlt_A"], ref["ldlt_rhs"]
+    f = handle.potrf(handle.upload(A))
+    assert_close(f.solve(rhs), ref["ldlt_solve"], RTOL)
+    assert abs(f.log_determinant() - float(ref["ldlt_logdet"])) < RTOL * abs(float(ref["ldlt_logdet"]))
+    assert_close(f.inverse_diagonal(), ref["ldlt_inverse_diagonal"], RTOL)
+    groups = [[0, 5, 9], [1], [100, 101, 102, 127], [64, 63]]
+    got = np.concatenate([b.ravel(order="F") for b in f.inverse_blocks(groups)])
+    assert_close(got, ref["ldlt_inverse_blocks"], RTOL)
+
+
+@pytest.mark.parametrize("n", [5, 64, 300, 700])
+def test_inverse_diagonal_and_blocks(handle, n):
+    A = spd(n, seed=3 * n)
+    f = handle.potrf(handle.upload(A))
+    inv = np.linalg.inv(A)
+    assert_close(f.inverse_diagonal(), np.diag(inv), 1e-8)
+    rng = np.random.default_rng(n)
+    perm = rng.permutation(n)
+    groups = [perm[: n // 3], perm[n // 3: n // 3 + 1], perm[n // 3 + 1:]]
+    for g, b in zip(groups, f.inverse_blocks(groups)):
+        assert_close(b, inv[np.ix_(g, g)], 1e-8)
+    want = Restate.inverse_blocks(A, groups)
+    for b, w in zip(f.inverse_blocks(groups), want):
+        assert_close(b, w, RTOL)
+
+
+def test_nll_known_answer(handle, golden):
+    """tests/test_evaluate.cc:34-63 through the device factor."""
+    t, _ = golden
+    k = t["nll_known_answer"]
+    f = handle.potrf(handle.upload(np.array(k["cov"])))
+    assert abs(f.nll(np.array(k["x"])) - k["value"]) < 1e-12
+
+
+def test_not_positive_definite_is_reported(handle):
+    A = spd(130, seed=1)
+    A[70, 70] = -1.0
+    with pytest.raises(capi.AbError) as e:
+        handle.potrf(handle.upload(A))
+    assert e.value.status == 4
+    f = handle.potrf(handle.upload(A), allow_not_pd=True)
+    assert not f.is_positive_definite() and f.info() == 70
+    with pytest.raises(capi.AbError):
+        f.solve(np.ones(130))
+    # NaN anywhere in the lower triangle -> reported, never UB (gp.hpp:66)
+    B = spd(200, seed=2)
+    B[150, 20] = np.nan
+    f = handle.potrf(handle.upload(B), allow_not_pd=True)
+    assert not f.is_positive_definite()
+
+
+# ---- exact GP (tests/test_gp.cc, tests/lib/albatross/test/test_models.cc) -----------------------
+
+@pytest.mark.parametrize("cid", GP_COVS)
+@pytest.mark.parametrize("tag", ["1", "3"])
+def test_gp_vs_reference_fixture(handle, golden, cid, tag):
+    _, ref = golden
+    ops, pp = prog(cid)
+    x, y, t = ref[f"gp_x{tag}"], ref[f"gp_y{tag}"], ref[f"gp_test{tag}"]
+    f, info = handle.gp_fit(ops, pp, x, y)
+    assert_close(info, ref[f"info{tag}_{cid}"], RTOL, "information")
+    nll = handle.gp_nll(ops, pp, x, y)
+    assert abs(nll - float(ref[f"nll{tag}_{cid}"])) <= RTOL * abs(float(ref[f"nll{tag}_{cid}"]))
+    assert_close(handle.gp_predict(f, ops, pp, x, info, t, MEAN)[0], ref[f"mean{tag}_{cid}"], RTOL)
+    m, v, _ = handle.gp_predict(f, ops, pp, x, info, t, MARGINAL)
+    assert_close(m, ref[f"mean{tag}_{cid}"], RTOL)
+    assert_close(v, ref[f"var{tag}_{cid}"], RTOL, "marginal variance")
+    m, _, c = handle.gp_predict(f, ops, pp, x, info, t, JOINT)
+    assert_close(c, ref[f"cov{tag}_{cid}"], RTOL, "joint covariance")
+    # leave-one-out and leave-one-group-out
+    _, offsets, indices = capi.group_indexers(group_keys(x, 0))
+    m, v, _, s = handle.gp_cv(f, y, info, offsets, indices, MARGINAL, want_score=True)
+    assert_close(m, ref[f"loo_mean{tag}_{cid}"], RTOL, "loo mean")
+    assert_close(v, ref[f"loo_var{tag}_{cid}"], RTOL, "loo var")
+    assert abs(s - float(ref[f"loo_score{tag}_{cid}"])) <= RTOL * abs(float(ref[f"loo_score{tag}_{cid}"]))
+    keys, offsets, indices = capi.group_indexers(group_keys(x, 1, 8))
+    m, v, _, s = handle.gp_cv(f, y, info, offsets, indices, MARGINAL, want_score=True)
+    assert_close(m, ref[f"logo_mean{tag}_{cid}"], RTOL, "logo mean")
+    assert_close(v, ref[f"logo_var{tag}_{cid}"], RTOL, "logo var")
+    assert abs(s - float(ref[f"logo_score{tag}_{cid}"])) <= RTOL * abs(float(ref[f"logo_score{tag}_{cid}"]))
+    m2, _, j, _ = handle.gp_cv(f, y, info, offsets, indices, JOINT)
+    assert_close(j, ref[f"logo_joint{tag}_{cid}"], RTOL, "logo joint")
+    assert_close(m2, m, 1e-13)
+    m3 = handle.gp_cv(f, y, info, offsets, indices, MEAN)[0]
+    assert_close(m3, m, 1e-13)
+
+
+def test_fit_adds_target_variance_but_nll_does_not(handle, golden):
+    """gp.hpp:65 vs gp.hpp:447-448."""
+    _, ref = golden
+    ops, pp = prog(6)
+    x, y, yvar, t = ref["gp_x1"], ref["gp_y1"], ref["gp_yvar"], ref["gp_test1"]
+    f, info = handle.gp_fit(ops, pp, x, y, yvar=yvar)
+    assert_close(info, ref["info1_6_yvar"], RTOL)
+    assert_close(handle.gp_predict(f, ops, pp, x, info, t, MARGINAL)[1], ref["var1_6_yvar"], RTOL)
+    assert abs(handle.gp_nll(ops, pp, x, y) - float(ref["nll1_6"])) <= RTOL * abs(float(ref["nll1_6"]))
+
+
+@pytest.mark.parametrize("n,dim", [(1, 1), (2, 3), (65, 1), (500, 3), (1500, 3)])
+def test_gp_against_restatement(handle, n, dim):
+    ops, pp = prog(8)
+    x = features(n, dim, seed=n)
+    y = targets(x)
+    t = features(9, dim, seed=99)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    assert_close(info, Restate.gp_fit(ops, pp, x, y)["information"], RTOL)
+    want_nll = Restate.gp_nll(ops, pp, x, y)
+    assert abs(handle.gp_nll(ops, pp, x, y) - want_nll) <= RTOL * max(1.0, abs(want_nll))
+    f2, info2, nll2 = handle.gp_fit_nll(ops, pp, x, y)
+    assert abs(nll2 - want_nll) <= RTOL * max(1.0, abs(want_nll))
+    assert_close(info2, info, 1e-13)
+    for what in (MEAN, MARGINAL, JOINT):
+        got = handle.gp_predict(f, ops, pp, x, info, t, what)
+        want = Restate.gp_predict(ops, pp, x, y, t, what)
+        for g, w in zip(got, want):
+            if w is not None:
+                assert_close(g, w, RTOL, f"predict {what}")
+
+
+def test_predict_training_points_and_order(handle):
+    """tests/test_gp.cc: predictions preserve order; mean at training points ~ targets."""
+    ops, pp = prog(6)
+    x = features(400, 1, 7)
+    y = targets(x)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    perm = np.random.default_rng(0).permutation(400)[:50]
+    a = handle.gp_predict(f, ops, pp, x, info, x[perm], MARGINAL)
+    b = handle.gp_predict(f, ops, pp, x, info, x[np.sort(perm)], MARGINAL)
+    order = np.argsort(perm)
+    assert_close(a[0][order], b[0], 1e-12)
+    assert_close(a[1][order], b[1], 1e-12)
+    assert np.max(np.abs(a[0] - y[perm])) < 0.2
+
+
+@pytest.mark.skipif(not Ref.available(), reason="oracle/_ref not shipped")
+def test_gp_against_live_reference_n2000(handle):
+    """The reference's own Eigen path at a size it finishes in seconds."""
+    cid = 6
+    ops, pp = prog(cid)
+    x = Ref.random_features(2000, 3, 0)
+    y = Ref.random_targets(x)
+    t = Ref.random_features(32, 3, 5)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    assert_close(info, Ref.gp_fit(cid, PARAMS[cid], x, y)["information"], RTOL)
+    want = Ref.gp_nll(cid, PARAMS[cid], x, y)[0]
+    assert abs(handle.gp_nll(ops, pp, x, y) - want) <= RTOL * abs(want)
+    m, v, _ = handle.gp_predict(f, ops, pp, x, info, t, MARGINAL)
+    rm, rv, _ = Ref.gp_predict(cid, PARAMS[cid], x, y, t, 1)
+    assert_close(m, rm, RTOL)
+    assert_close(v, rv, RTOL)
+
+
+# ---- size-independent properties at scale -------------------------------------------------------
+
+def test_large_fit_residual_and_consistency(handle):
+    """N=8192: K alpha = y to backward-error level; NLL pieces consistent with the factor."""
+    ops, pp = prog(6)
+    n = 8192
+    x = features(n, 3, 0)
+    y = targets(x)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    K = handle.gram_sym(ops, pp, x).download()
+    resid = np.linalg.norm(K @ info - y) / (np.linalg.norm(K, 2) * np.linalg.norm(info))
+    assert resid < 1e-14, resid
+    nll = handle.gp_nll(ops, pp, x, y)
+    want = 0.5 * (f.log_determinant() + y @ info + n * np.log(2 * np.pi))
+    assert abs(nll - want) <= 1e-10 * abs(want)
+    sign, logdet = np.linalg.slogdet(K)
+    assert sign > 0 and abs(f.log_determinant() - logdet) <= 1e-9 * abs(logdet)
+    # leave-one-out vs the closed form on a subset of points
+    _, offsets, indices = capi.group_indexers(np.arange(n))
+    m, v, _, _ = handle.gp_cv(f, y, info, offsets, indices, MARGINAL)
+    Kinv_diag = np.diag(np.linalg.inv(K))
+    assert_close(v, 1.0 / Kinv_diag, 1e-8)
+    assert_close(m, y - info / Kinv_diag, 1e-8)
