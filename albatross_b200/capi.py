@@ -57,7 +57,7 @@ SYMBOLS = [
     "ab_factor_sqrt_solve", "ab_factor_logdet", "ab_factor_nll", "ab_factor_inverse_diagonal",
     "ab_factor_inverse_blocks", "ab_factor_export_packed", "ab_gp_fit", "ab_gp_nll",
     "ab_gp_fit_nll", "ab_gp_predict", "ab_gp_cv", "ab_gp_fit_d", "ab_gp_nll_d",
-    "ab_group_indexers",
+    "ab_group_indexers", "ab_gemm",
 ]
 
 
@@ -295,6 +295,16 @@ class Handle:
         _check(lib().ab_matrix_upload(self.ptr, _d(a), C.c_int64(a.shape[0]),
                                       C.c_int64(a.shape[1]), C.byref(out)))
         return Matrix(self, out)
+
+    def alloc(self, rows, cols):
+        out = C.c_void_p()
+        _check(lib().ab_matrix_alloc(self.ptr, C.c_int64(rows), C.c_int64(cols), C.byref(out)))
+        return Matrix(self, out)
+
+    def gemm(self, A, B, Cm, alpha=1.0, beta=0.0, trans_a=False, trans_b=False, lower=False):
+        flags = (1 if trans_a else 0) | (2 if trans_b else 0) | (4 if lower else 0)
+        _check(lib().ab_gemm(self.ptr, C.c_uint32(flags), C.c_double(alpha), A.ptr, B.ptr,
+                             C.c_double(beta), Cm.ptr))
 
     def upload_features(self, feats):
         """Features (n, dim) -> dim x n device matrix (AoS preserved)."""

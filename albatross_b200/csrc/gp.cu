@@ -925,6 +925,30 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
   return AB_OK;
 }
 
+// ---- dense building block ---------------------------------------------------------------------
+
+int ab_gemm(ab_handle h, uint32_t flags, double alpha, ab_matrix A, ab_matrix B, double beta,
+            ab_matrix C) {
+  AB_REQUIRE(h != nullptr && A != nullptr && B != nullptr && C != nullptr, "null");
+  const bool ta = flags & AB_GEMM_TRANS_A;
+  const bool tb = flags & AB_GEMM_TRANS_B;
+  const int64_t m = ta ? A->cols : A->rows;
+  const int64_t k = ta ? A->rows : A->cols;
+  const int64_t kb = tb ? B->cols : B->rows;
+  const int64_t n = tb ? B->rows : B->cols;
+  AB_REQUIRE(k == kb && C->rows == m && C->cols == n, "GEMM shapes do not conform");
+  AB_REQUIRE(C != A && C != B, "ab_gemm does not work in place");
+  Lock lock(h);
+  timings_reset(h);
+  phase_begin(h, PH_FACTOR);
+  unsigned f = (ta ? GEMM_TRANS_A : 0u) | (tb ? GEMM_TRANS_B : 0u) |
+               ((flags & AB_GEMM_LOWER) ? GEMM_LOWER : 0u);
+  int s = gemm(h, f, m, n, k, alpha, view(A), view(B), beta, view(C));
+  phase_end(h, PH_FACTOR);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return s;
+}
+
 // ---- integer contract -------------------------------------------------------------------------
 
 int ab_group_indexers(const int64_t *item_keys, int64_t n, int64_t *keys, int64_t *offsets,

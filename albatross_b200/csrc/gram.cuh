@@ -5,27 +5,35 @@
 
 namespace ab {
 
-// Leaf kinds on the device (host pre-digests hyper-parameters into c0 / amp).
+// Leaf kinds on the device.  The four radial kernels of radial.hpp share one code path:
+//     k = amp * poly * exp(u),   u = a2 * d^2  or  a1 * d   (u <= 0),
+//     poly = 1 [+ b1 * d [+ b2 * d^2]]
+//   SquaredExponential  a2 = -1/l^2
+//   Exponential         a1 = -1/l
+//   Matern32            a1 = -sqrt(3)/l, b1 = sqrt(3)/l
+//   Matern52            a1 = -sqrt(5)/l, b1 = sqrt(5)/l, b2 = 5/(3 l^2)
 enum DevKind : int {
-  DK_SE = 1,    // amp * exp(c0 * d^2),            c0 = -1/l^2
-  DK_EXP = 2,   // amp * exp(c0 * d),              c0 = -1/l
-  DK_M32 = 3,   // amp * (1 + s) exp(-s),          s = c0 * d, c0 = sqrt(3)/l
-  DK_M52 = 4,   // amp * (1 + s + s^2/3) exp(-s),  s = c0 * d, c0 = sqrt(5)/l
-  DK_CONST = 5, // amp
-  DK_NOISE = 6, // amp if x == y (all coordinates) else 0
+  DK_RADIAL = 1,
+  DK_CONST = 2, // amp
+  DK_NOISE = 3, // amp if x == y (all coordinates) else 0
+  DK_ZERO = 4,  // radial leaf with length_scale <= 0 (radial.hpp:28-30): contributes 0
   DK_SUM = 7,   // stack mode only
-  DK_PROD = 8,  // stack mode only
-  DK_ZERO = 9   // radial leaf with length_scale <= 0 (radial.hpp:28-30): contributes 0
+  DK_PROD = 8   // stack mode only
 };
 
-// flags for the sum-of-products form
-enum : int { DF_TERM_START = 1, DF_TERM_END = 2, DF_FIRST_TERM = 4 };
+enum : int {
+  DF_TERM_START = 1,
+  DF_TERM_END = 2,
+  DF_FIRST_TERM = 4,
+  DF_USES_DIST = 8, // u = a1 * d (else u = a2 * d^2)
+  DF_POLY_D1 = 16,  // poly has the b1 * d term
+  DF_POLY_D2 = 32   // poly has the b2 * d^2 term
+};
 
 struct DevOp {
   int kind;
   int flags;
-  double c0;
-  double amp;
+  double a2, a1, b2, b1, amp;
 };
 
 // mode 0: "sum of products" — expr := term (+ term)*, term := leaf (* leaf)*, evaluated left to

@@ -246,6 +246,20 @@ AB_API int ab_gp_fit_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats
 AB_API int ab_gp_nll_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
                 double *nll);
 
+/* ---- dense building block -------------------------------------------------------------------- */
+
+#define AB_GEMM_TRANS_A 1u /* op(A) = A^T */
+#define AB_GEMM_TRANS_B 2u /* op(B) = B^T */
+#define AB_GEMM_LOWER 4u   /* C square: only the tiles touching the lower triangle are computed */
+/*
+ * C = alpha * op(A) * op(B) + beta * C on device-resident matrices (the DMMA kernel that performs
+ * every O(n^3) step of the factorisation and the solves).  Exposed for callers that compose their
+ * own block algebra (BlockSymmetric updates, src/linalg/block_symmetric.hpp:46-133) and for
+ * benchmarking the kernel in isolation.
+ */
+AB_API int ab_gemm(ab_handle h, uint32_t flags, double alpha, ab_matrix A, ab_matrix B, double beta,
+            ab_matrix C);
+
 /* ---- integer contract helpers (host; bit-exact with src/indexing/) -------------------------- */
 
 /*
