@@ -57,8 +57,13 @@ SYMBOLS = [
     "ab_factor_sqrt_solve", "ab_factor_logdet", "ab_factor_nll", "ab_factor_inverse_diagonal",
     "ab_factor_inverse_blocks", "ab_factor_export_packed", "ab_gp_fit", "ab_gp_nll",
     "ab_gp_fit_nll", "ab_gp_predict", "ab_gp_cv", "ab_gp_fit_d", "ab_gp_nll_d",
-    "ab_group_indexers", "ab_gemm",
+    "ab_group_indexers", "ab_gemm", "ab_gp_cv_shard",
+    "ab_sparse_fit", "ab_sparse_free", "ab_sparse_info", "ab_sparse_log_likelihood",
+    "ab_sparse_predict", "ab_sparse_export_R",
+    "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
+    "ab_dist_factor_free", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
 ]
+DIST_ID_BYTES = 128
 
 
 def lib():
@@ -428,6 +433,191 @@ class Handle:
                               C.c_int64(len(sizes)), C.c_int(what), _d(mean), _d(var), _d(joint),
                               C.byref(score) if want_score else None))
         return mean, var, joint, (score.value if want_score else None)
+
+    def gp_cv_shard(self, factor, y, information, offsets, indices, what, shard, nshards,
+                    want_score=False):
+        y, info = _vec(y), _vec(information)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        n = len(y)
+        mean = np.empty(n)
+        var = np.empty(n) if what == MARGINAL else None
+        score = C.c_double()
+        _check(lib().ab_gp_cv_shard(self.ptr, factor.ptr, _d(y), _d(info), _i(indices),
+                                    _i(offsets), C.c_int64(len(offsets) - 1), C.c_int(what),
+                                    C.c_int(shard), C.c_int(nshards), _d(mean), _d(var),
+                                    C.byref(score) if want_score else None))
+        return mean, var, (score.value if want_score else None)
+
+    # -- sparse GP ----------------------------------------------------------------------------
+    def _sparse_args(self, ops, params, feats, y, yvar, inducing, offsets, indices,
+                     measurement_nugget, inducing_nugget):
+        prog, nops = program(ops, params)
+        x, u = _feats(feats), _feats(inducing)
+        y, yv = _vec(y), _vec(yvar)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        keep = (prog, x, u, y, yv, offsets, indices)
+        args = (self.ptr, prog, nops, _d(x), C.c_int64(x.shape[0]), C.c_int(x.shape[1]), _d(y),
+                _d(yv), _d(u), C.c_int64(u.shape[0]), _i(indices), _i(offsets),
+                C.c_int64(len(offsets) - 1), C.c_double(measurement_nugget),
+                C.c_double(inducing_nugget))
+        return args, keep, u.shape[0]
+
+    def sparse_fit(self, ops, params, feats, y, inducing, offsets, indices, yvar=None,
+                   measurement_nugget=1e-8, inducing_nugget=1e-8):
+        """Returns (SparseFit, information[m], log_likelihood)."""
+        args, keep, m = self._sparse_args(ops, params, feats, y, yvar, inducing, offsets, indices,
+                                          measurement_nugget, inducing_nugget)
+        out = C.c_void_p()
+        info = np.empty(m)
+        ll = C.c_double()
+        _check(lib().ab_sparse_fit(*args, C.byref(out), _d(info), C.byref(ll)))
+        del keep
+        return SparseFit(self, out), info, ll.value
+
+    def sparse_log_likelihood(self, ops, params, feats, y, inducing, offsets, indices, yvar=None,
+                              measurement_nugget=1e-8, inducing_nugget=1e-8):
+        args, keep, _ = self._sparse_args(ops, params, feats, y, yvar, inducing, offsets, indices,
+                                          measurement_nugget, inducing_nugget)
+        ll = C.c_double()
+        _check(lib().ab_sparse_log_likelihood(*args, C.byref(ll)))
+        del keep
+        return ll.value
+
+    # -- distributed group --------------------------------------------------------------------
+    def dist_init(self, rank, world, unique_id):
+        buf = (C.c_char * DIST_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _check(lib().ab_dist_init(self.ptr, C.c_int(rank), C.c_int(world), buf))
+
+    def dist_init_from_torch(self):
+        """Bootstraps the library's own NCCL communicator through an initialised torch.distributed
+        process group (albatross_b200/dist.py)."""
+        from . import dist
+
+        return dist.bootstrap(self)
+
+    def dist_finalize(self):
+        _check(lib().ab_dist_finalize(self.ptr))
+
+    def dist_info(self):
+        r, w = C.c_int(), C.c_int()
+        _check(lib().ab_dist_info(self.ptr, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def dist_gp_fit(self, ops, params, feats, y, yvar=None, nb=0, want_information=True):
+        """All ranks call with identical arguments.  Returns (DistFactor, information, nll)."""
+        prog, nops = program(ops, params)
+        x = _feats(feats)
+        y, yv = _vec(y), _vec(yvar)
+        info = np.empty(x.shape[0]) if want_information else None
+        out = C.c_void_p()
+        nll = C.c_double()
+        _check(lib().ab_dist_gp_fit(self.ptr, prog, nops, _d(x), C.c_int64(x.shape[0]),
+                                    C.c_int(x.shape[1]), _d(y), _d(yv), C.c_int64(nb),
+                                    C.byref(out), _d(info), C.byref(nll)))
+        return DistFactor(self, out), info, nll.value
+
+    def dist_gram_rows(self, ops, params, feats):
+        """This rank's row block of the symmetric Gram: returns (row0, Matrix[rows x n])."""
+        prog, nops = program(ops, params)
+        x = _feats(feats)
+        r0, nr = C.c_int64(), C.c_int64()
+        out = C.c_void_p()
+        _check(lib().ab_dist_gram_rows(self.ptr, prog, nops, _d(x), C.c_int64(x.shape[0]),
+                                       C.c_int(x.shape[1]), C.byref(r0), C.byref(nr),
+                                       C.byref(out)))
+        return r0.value, Matrix(self, out)
+
+    def dist_gp_cv(self, factor, y, information, offsets, indices, what, want_score=False):
+        y, info = _vec(y), _vec(information)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int64)
+        n = len(y)
+        mean = np.empty(n)
+        var = np.empty(n) if what == MARGINAL else None
+        score = C.c_double()
+        _check(lib().ab_dist_gp_cv(self.ptr, factor.ptr, _d(y), _d(info), _i(indices), _i(offsets),
+                                   C.c_int64(len(offsets) - 1), C.c_int(what), _d(mean), _d(var),
+                                   C.byref(score) if want_score else None))
+        return mean, var, (score.value if want_score else None)
+
+
+class SparseFit:
+    """Device-resident Fit<SparseGPFit> (inducing features, K_uu factor, R factors, information)."""
+
+    def __init__(self, handle, ptr):
+        self.h, self.ptr = handle, ptr
+
+    @property
+    def m(self):
+        m = C.c_int64()
+        _check(lib().ab_sparse_info(self.ptr, C.byref(m), None))
+        return m.value
+
+    @property
+    def log_likelihood(self):
+        ll = C.c_double()
+        _check(lib().ab_sparse_info(self.ptr, None, C.byref(ll)))
+        return ll.value
+
+    def predict(self, ops, params, test_feats, what):
+        prog, nops = program(ops, params)
+        t = _feats(test_feats)
+        p = t.shape[0]
+        mean = np.empty(p)
+        var = np.empty(p) if what == MARGINAL else None
+        cov = np.empty((p, p), order="F") if what == JOINT else None
+        _check(lib().ab_sparse_predict(self.h.ptr, self.ptr, prog, nops, _d(t), C.c_int64(p),
+                                       C.c_int(what), _d(mean), _d(var), _d(cov)))
+        return mean, var, cov
+
+    def export_R(self):
+        m = self.m
+        R = np.empty((m, m), order="F")
+        _check(lib().ab_sparse_export_R(self.h.ptr, self.ptr, _d(R)))
+        return R
+
+    def free(self):
+        if self.ptr:
+            lib().ab_sparse_free(self.h.ptr, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DistFactor:
+    """This rank's shard of a block-column-cyclic Cholesky factor."""
+
+    def __init__(self, handle, ptr):
+        self.h, self.ptr = handle, ptr
+
+    def free(self):
+        if self.ptr:
+            lib().ab_dist_factor_free(self.h.ptr, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def dist_unique_id():
+    buf = (C.c_char * DIST_ID_BYTES)()
+    _check(lib().ab_dist_unique_id(buf))
+    return bytes(buf.raw)
+
+
+def dist_block_owner(block, world):
+    r, lb = C.c_int(), C.c_int64()
+    _check(lib().ab_dist_block_owner(C.c_int64(block), C.c_int(world), C.byref(r), C.byref(lb)))
+    return r.value, lb.value
 
 
 def device_count():

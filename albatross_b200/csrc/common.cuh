@@ -104,6 +104,13 @@ struct ab_handle_s {
   // pinned staging for host<->device vector traffic
   void *h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  // distributed group (dist.cu): one process per GPU, NCCL communicator over NVLink / NVSwitch
+  void *comm = nullptr; // ncclComm_t
+  int rank = 0;
+  int world = 1;
+  cudaStream_t comm_stream = nullptr; // high-priority stream for panel broadcasts
+  cudaEvent_t ev_bcast[2] = {nullptr, nullptr};
+  cudaEvent_t ev_ready = nullptr, ev_free = nullptr;
 };
 
 namespace ab {

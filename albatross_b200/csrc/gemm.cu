@@ -29,6 +29,11 @@ __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc,
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc),
                "r"(src_bytes));
 }
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc, int src_bytes) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc),
+               "r"(src_bytes));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
@@ -45,9 +50,34 @@ __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, doubl
 //   KMAJOR == true : element (i, kk) at g[kk + i * ld]   -> smem[i * LDK + kk]
 // i in [0, BM) relative to the tile; rows >= extent and k >= kextent are zero-filled (rows beyond
 // the extent only ever feed outputs that are not stored, but k beyond kextent must contribute 0).
+// vec == false: the operand is only 8-byte aligned (odd row offset of a sub-view or odd leading
+// dimension): the same chunks are moved as two predicated 8-byte copies.
 template <bool KMAJOR>
 __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t ld, int64_t i0,
-                                          int64_t extent, int64_t k0, int64_t kextent, int tid) {
+                                          int64_t extent, int64_t k0, int64_t kextent, int tid,
+                                          bool vec) {
+  if (!vec) {
+#pragma unroll
+    for (int it = 0; it < (BK * BM / 2) / GEMM_THREADS; ++it) {
+      const int chunk = tid + it * GEMM_THREADS;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int i, kk;
+        if (!KMAJOR) {
+          kk = chunk / (BM / 2);
+          i = (chunk % (BM / 2)) * 2 + e;
+        } else {
+          i = chunk / (BK / 2);
+          kk = (chunk % (BK / 2)) * 2 + e;
+        }
+        const bool ok = (i0 + i < extent) && (k0 + kk < kextent);
+        const double *src =
+            ok ? (KMAJOR ? g + (k0 + kk) + (i0 + i) * ld : g + (i0 + i) + (k0 + kk) * ld) : g;
+        cp_async8(KMAJOR ? smem + i * LDK + kk : smem + kk * LDMN + i, src, ok ? 8 : 0);
+      }
+    }
+    return;
+  }
   if (!KMAJOR) {
 #pragma unroll
     for (int it = 0; it < (BK * BM / 2) / GEMM_THREADS; ++it) {
@@ -82,7 +112,10 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int64_t lda,
             const double *B, int64_t ldb, double beta, double *C,
-            int64_t ldc, int tiles_m, int lower, int vec_ok) {
+            int64_t ldc, int tiles_m, int lower, int vec_flags) {
+  const int vec_ok = vec_flags & 1;      // C: 16-byte epilogue
+  const bool a_vec = vec_flags & 2;      // A: 16-byte cp.async
+  const bool b_vec = vec_flags & 4;      // B: 16-byte cp.async
   constexpr bool A_KMAJOR = TA;
   constexpr bool B_KMAJOR = !TB;
   constexpr int A_ELEMS = A_KMAJOR ? TILE_K_ELEMS : TILE_MN_ELEMS;
@@ -132,8 +165,10 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
-      load_tile<A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(s) * BK, k, tid);
-      load_tile<B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(s) * BK, k, tid);
+      load_tile<A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(s) * BK, k, tid,
+                          a_vec);
+      load_tile<B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(s) * BK, k, tid,
+                          b_vec);
     }
     cp_async_commit();
   }
@@ -145,8 +180,10 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
       const int nt = kt + STAGES - 1;
       if (nt < ktiles) {
         const int s = nt % STAGES;
-        load_tile<A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(nt) * BK, k, tid);
-        load_tile<B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(nt) * BK, k, tid);
+        load_tile<A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(nt) * BK, k, tid,
+                            a_vec);
+        load_tile<B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(nt) * BK, k, tid,
+                            b_vec);
       }
       cp_async_commit();
     }
@@ -233,15 +270,99 @@ static int launch(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, d
   const int64_t tn = (n + BN - 1) / BN;
   const int64_t tiles = lower ? tm * (tm + 1) / 2 : tm * tn;
   AB_REQUIRE(tiles < (int64_t(1) << 31), "GEMM grid too large");
-  const int vec_ok = (reinterpret_cast<uintptr_t>(C.p) % 16 == 0) && (C.ld % 2 == 0);
-  AB_REQUIRE(reinterpret_cast<uintptr_t>(A.p) % 16 == 0 && A.ld % 2 == 0 &&
-                 reinterpret_cast<uintptr_t>(B.p) % 16 == 0 && B.ld % 2 == 0,
-             "GEMM operands must be 16-byte aligned with even leading dimension");
+  const auto aligned16 = [](const MatView &M) {
+    return reinterpret_cast<uintptr_t>(M.p) % 16 == 0 && M.ld % 2 == 0;
+  };
+  const int vec_ok = (aligned16(C) ? 1 : 0) | (aligned16(A) ? 2 : 0) | (aligned16(B) ? 4 : 0);
   gemm_kernel<TA, TB><<<static_cast<unsigned>(tiles), GEMM_THREADS, smem, h->stream>>>(
       m, n, k, alpha, A.p, A.ld, B.p, B.ld, beta, C.p, C.ld, static_cast<int>(tm), lower ? 1 : 0,
       vec_ok);
   AB_LAUNCHED(h);
   return AB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// n == 1: matrix-vector products (HBM-bound; the 128 x 128 MMA tiling would leave 127/128 of the
+// tensor work idle and, for op(A) = A^T, only m/128 CTAs in flight)
+// ------------------------------------------------------------------------------------------------
+
+constexpr int GEMV_ROWS = 32;
+constexpr int GEMV_WARPS = 8;
+
+// c[m] = alpha * A[m x k] b[k] + beta * c ; A column-major.  CTA = 32 rows; warp w walks the columns
+// kk = w, w + 8, ...; lane = row (256 contiguous bytes per warp load); deterministic reduction.
+__global__ void __launch_bounds__(GEMV_ROWS *GEMV_WARPS)
+gemv_n_kernel(int64_t m, int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
+              const double *__restrict__ b, double beta, double *c) {
+  __shared__ double red[GEMV_WARPS][GEMV_ROWS];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t row = blockIdx.x * static_cast<int64_t>(GEMV_ROWS) + lane;
+  double acc0 = 0., acc1 = 0., acc2 = 0., acc3 = 0.;
+  if (row < m) {
+    const double *a = A + row;
+    int64_t kk = warp;
+    for (; kk + 3 * GEMV_WARPS < k; kk += 4 * GEMV_WARPS) {
+      acc0 = fma(a[kk * lda], b[kk], acc0);
+      acc1 = fma(a[(kk + GEMV_WARPS) * lda], b[kk + GEMV_WARPS], acc1);
+      acc2 = fma(a[(kk + 2 * GEMV_WARPS) * lda], b[kk + 2 * GEMV_WARPS], acc2);
+      acc3 = fma(a[(kk + 3 * GEMV_WARPS) * lda], b[kk + 3 * GEMV_WARPS], acc3);
+    }
+    for (; kk < k; kk += GEMV_WARPS) {
+      acc0 = fma(a[kk * lda], b[kk], acc0);
+    }
+  }
+  red[warp][lane] = (acc0 + acc1) + (acc2 + acc3);
+  __syncthreads();
+  if (warp == 0 && row < m) {
+    double total = 0.;
+#pragma unroll
+    for (int w = 0; w < GEMV_WARPS; ++w) {
+      total += red[w][lane];
+    }
+    double v = alpha * total;
+    if (beta != 0.) {
+      v = fma(beta, c[row], v);
+    }
+    c[row] = v;
+  }
+}
+
+// c[m] = alpha * A^T b + beta * c ; A stored k x m (k contiguous).  One CTA per output element.
+__global__ void __launch_bounds__(256)
+gemv_t_kernel(int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
+              const double *__restrict__ b, double beta, double *c) {
+  __shared__ double red[8];
+  const double *a = A + blockIdx.x * lda;
+  double acc0 = 0., acc1 = 0.;
+  int64_t i = threadIdx.x;
+  for (; i + 256 < k; i += 512) {
+    acc0 = fma(a[i], b[i], acc0);
+    acc1 = fma(a[i + 256], b[i + 256], acc1);
+  }
+  for (; i < k; i += 256) {
+    acc0 = fma(a[i], b[i], acc0);
+  }
+  double v = acc0 + acc1;
+  for (int o = 16; o > 0; o >>= 1) {
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      total += red[w];
+    }
+    double out = alpha * total;
+    if (beta != 0.) {
+      out = fma(beta, c[blockIdx.x], out);
+    }
+    c[blockIdx.x] = out;
+  }
 }
 
 int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double alpha, MatView A,
@@ -254,6 +375,19 @@ int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double
   const bool lower = flags & GEMM_LOWER;
   if (lower) {
     AB_REQUIRE(m == n, "GEMM_LOWER needs a square C");
+  }
+  if (n == 1 && !tb && m > 1 && C.p != B.p && C.p != A.p && k > 0) {
+    // B is a contiguous k-vector (op(B) = B, one column)
+    if (ta) {
+      gemv_t_kernel<<<static_cast<unsigned>(m), 256, 0, h->stream>>>(k, alpha, A.p, A.ld, B.p,
+                                                                      beta, C.p);
+    } else {
+      const unsigned blocks = static_cast<unsigned>((m + GEMV_ROWS - 1) / GEMV_ROWS);
+      gemv_n_kernel<<<blocks, GEMV_ROWS * GEMV_WARPS, 0, h->stream>>>(m, k, alpha, A.p, A.ld, B.p,
+                                                                      beta, C.p);
+    }
+    AB_LAUNCHED(h);
+    return AB_OK;
   }
   if (ta && tb) {
     return launch<true, true>(h, lower, m, n, k, alpha, A, B, beta, C);

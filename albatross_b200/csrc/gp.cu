@@ -2,8 +2,7 @@
 //
 // Each entry point cites the reference routine it replaces in the header; this file only sequences
 // device kernels (gram.cu, gemm.cu, linalg.cu) on the handle's stream and moves results to the host.
-#include "gram.cuh"
-#include "linalg.cuh"
+#include "internal.cuh"
 
 #include <algorithm>
 #include <climits>
@@ -13,134 +12,7 @@
 #include <vector>
 
 namespace ab {
-
-int gram_sym_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *feats, uint32_t flags,
-                    ab_matrix_s **out);
-int gram_cross_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *fx,
-                      const ab_matrix_s *fy, ab_matrix_s **out);
-int gram_diag_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *feats, double *d_out);
-int upload_features(ab_handle_s *h, const double *feats, int64_t n, int dim, ab_matrix_s **out);
-
 namespace {
-
-// RAII for temporaries so that every early return recycles device buffers.
-struct Scope {
-  explicit Scope(ab_handle_s *h) : h(h) {}
-  ~Scope() {
-    for (auto *m : mats) {
-      matrix_delete(h, m);
-    }
-    for (auto &b : bufs) {
-      dev_release(h, b.first, b.second);
-    }
-  }
-  ab_matrix_s *own(ab_matrix_s *m) {
-    mats.push_back(m);
-    return m;
-  }
-  void disown(ab_matrix_s *m) { mats.erase(std::remove(mats.begin(), mats.end(), m), mats.end()); }
-  int alloc(size_t bytes, void **out) {
-    int s = dev_alloc(h, bytes, out);
-    if (s == AB_OK) {
-      bufs.emplace_back(*out, bytes);
-    }
-    return s;
-  }
-  ab_handle_s *h;
-  std::vector<ab_matrix_s *> mats;
-  std::vector<std::pair<void *, size_t>> bufs;
-};
-
-MatView view(const ab_matrix_s *m) { return MatView{m->d, m->ld}; }
-
-int upload_bytes(ab_handle_s *h, Scope &sc, const void *host, size_t bytes, void **dev) {
-  AB_TRY(sc.alloc(bytes, dev));
-  if (bytes > 0) {
-    AB_CUDA(cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, h->stream));
-  }
-  return AB_OK;
-}
-
-int download_bytes(ab_handle_s *h, const void *dev, size_t bytes, void *host) {
-  if (bytes > 0) {
-    AB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
-  }
-  AB_CUDA(cudaStreamSynchronize(h->stream));
-  return AB_OK;
-}
-
-int new_factor(ab_handle_s *h, ab_matrix_s *m, ab_factor_s **out) {
-  AB_REQUIRE(m->rows == m->cols, "factorisation needs a square matrix");
-  auto *f = new ab_factor_s();
-  f->m = m;
-  f->n = m->rows;
-  const int64_t nblocks = (f->n + LEAF - 1) / LEAF;
-  f->dinv_bytes = static_cast<size_t>(nblocks < 1 ? 1 : nblocks) * LEAF * LEAF * sizeof(double);
-  void *p = nullptr;
-  int s = dev_alloc(h, f->dinv_bytes, &p);
-  if (s != AB_OK) {
-    delete f;
-    return s;
-  }
-  f->dinv = static_cast<double *>(p);
-  *out = f;
-  return AB_OK;
-}
-
-void delete_factor(ab_handle_s *h, ab_factor_s *f) {
-  if (f == nullptr) {
-    return;
-  }
-  matrix_delete(h, f->m);
-  dev_release(h, f->dinv, f->dinv_bytes);
-  delete f;
-}
-
-// Factor `m` in place (consumed) and report the first bad pivot.
-int factorize(ab_handle_s *h, ab_matrix_s *m, ab_factor_s **out) {
-  ab_factor_s *f = nullptr;
-  int s = new_factor(h, m, &f);
-  if (s != AB_OK) {
-    matrix_delete(h, m);
-    return s;
-  }
-  h->h_flags[0] = INT_MAX;
-  cudaMemcpyAsync(h->d_flags, h->h_flags, sizeof(int), cudaMemcpyHostToDevice, h->stream);
-  s = potrf(h, view(m), f->n, f->dinv, h->d_flags);
-  if (s == AB_OK) {
-    cudaError_t e =
-        cudaMemcpyAsync(h->h_flags, h->d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) {
-      e = cudaStreamSynchronize(h->stream);
-    }
-    if (e != cudaSuccess) {
-      set_error("factorisation failed: %s", cudaGetErrorString(e));
-      s = AB_ERR_CUDA;
-    }
-  }
-  if (s != AB_OK) {
-    delete_factor(h, f);
-    return s;
-  }
-  f->bad_pivot = h->h_flags[0] == INT_MAX ? -1 : h->h_flags[0];
-  *out = f;
-  if (f->bad_pivot >= 0) {
-    set_error("matrix is not positive definite: pivot %lld is <= 0 or NaN",
-              static_cast<long long>(f->bad_pivot));
-    return AB_ERR_NOT_PD;
-  }
-  return AB_OK;
-}
-
-int require_usable(const ab_factor_s *f) {
-  AB_REQUIRE(f != nullptr && f->m != nullptr, "null factor");
-  if (f->bad_pivot >= 0) {
-    set_error("factor is not usable: matrix was not positive definite (pivot %lld)",
-              static_cast<long long>(f->bad_pivot));
-    return AB_ERR_NOT_PD;
-  }
-  return AB_OK;
-}
 
 // W <- L^-1 (lower triangular, W's strict upper triangle must already be zero).
 // T: workspace of at least ceil(n/2) x ceil(n/2) (+LEAF slack) doubles with leading dimension ldt.
@@ -183,6 +55,13 @@ __global__ void gather_cols_kernel(const double *W, int64_t ldw, int64_t row0, i
   const int64_t c = blockIdx.y;
   if (r < rows) {
     G[r + c * ldg] = W[row0 + r + idx[c] * ldw];
+  }
+}
+
+__global__ void set_diag_one_kernel(double *G, int64_t ldg, int64_t k) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c < k) {
+    G[c + c * ldg] = 1.;
   }
 }
 
@@ -441,20 +320,43 @@ int ab_factor_inverse_diagonal(ab_handle h, ab_factor f, double *out) {
   return download_bytes(h, d, static_cast<size_t>(f->n) * sizeof(double), out);
 }
 
-// (K^-1)_gg = W[:, g]^T W[:, g] written to dA (k x k, leading dimension ldA); W = L^-1.
-static int inverse_block_device(ab_handle h, const ab_matrix_s *W, const int64_t *d_idx,
-                                const int64_t *h_idx, int64_t k, ab_matrix_s *G, MatView A) {
-  const int64_t n = W->rows;
+__global__ void unit_columns_kernel(double *G, int64_t ldg, int64_t row0, const int64_t *idx,
+                                    int64_t k) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c < k) {
+    G[idx[c] - row0 + c * ldg] = 1.;
+  }
+}
+
+// (K^-1)_gg = W[:, g]^T W[:, g] written to A (k x k); W = L^-1.  With W == nullptr the k columns
+// of L^-1 are produced on the fly by a triangular solve on unit vectors (rows above the smallest
+// index are structurally zero and skipped): the form used when folds are sharded over GPUs and no
+// rank wants the whole inverse factor.
+static int inverse_block_device(ab_handle h, const ab_factor_s *f, const ab_matrix_s *W,
+                                const int64_t *d_idx, const int64_t *h_idx, int64_t k,
+                                ab_matrix_s *G, MatView A) {
+  const int64_t n = f->n;
   int64_t row0 = n;
   for (int64_t i = 0; i < k; ++i) {
     AB_REQUIRE(h_idx[i] >= 0 && h_idx[i] < n, "group index out of range");
     row0 = std::min(row0, h_idx[i]);
   }
-  row0 = row0 / 2 * 2; // keep 16-byte alignment of the gathered panel rows
+  if (W != nullptr) {
+    row0 = row0 / 2 * 2; // keep 16-byte alignment of the gathered panel rows
+    const int64_t rows = n - row0;
+    const dim3 grid(static_cast<unsigned>((rows + 255) / 256), static_cast<unsigned>(k));
+    gather_cols_kernel<<<grid, 256, 0, h->stream>>>(W->d, W->ld, row0, rows, d_idx, G->d, G->ld);
+    AB_LAUNCHED(h);
+    return gemm(h, GEMM_TRANS_A, k, k, rows, 1., view(G), view(G), 0., A);
+  }
+  row0 = row0 / LEAF * LEAF; // start the solve on a leaf boundary so that dinv blocks line up
   const int64_t rows = n - row0;
-  const dim3 grid(static_cast<unsigned>((rows + 255) / 256), static_cast<unsigned>(k));
-  gather_cols_kernel<<<grid, 256, 0, h->stream>>>(W->d, W->ld, row0, rows, d_idx, G->d, G->ld);
+  AB_TRY(fill(h, view(G), rows, k, 0.));
+  unit_columns_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, h->stream>>>(
+      G->d, G->ld, row0, d_idx, k);
   AB_LAUNCHED(h);
+  AB_TRY(trsm_left_lower(h, view(f->m).sub(row0, row0), f->dinv + (row0 / LEAF) * LEAF * LEAF,
+                         rows, view(G), k));
   return gemm(h, GEMM_TRANS_A, k, k, rows, 1., view(G), view(G), 0., A);
 }
 
@@ -486,7 +388,7 @@ int ab_factor_inverse_blocks(ab_handle h, ab_factor f, const int64_t *indices,
   double *cursor = out;
   for (int64_t g = 0; g < ngroups; ++g) {
     const int64_t k = offsets[g + 1] - offsets[g];
-    AB_TRY(inverse_block_device(h, W, static_cast<int64_t *>(d_idx) + offsets[g],
+    AB_TRY(inverse_block_device(h, f, W, static_cast<int64_t *>(d_idx) + offsets[g],
                                 indices + offsets[g], k, G, view(A)));
     AB_TRY(download(h, A, 0, 0, k, k, cursor));
     cursor += k * k;
@@ -749,22 +651,36 @@ int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const d
   return download(h, m, 0, 0, p, 1, mean);
 }
 
-int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *information,
-             const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
-             double *mean, double *var, double *joint, double *score) {
-  AB_REQUIRE(h != nullptr && y != nullptr && information != nullptr && indices != nullptr &&
-                 offsets != nullptr && mean != nullptr && ngroups >= 0,
-             "null");
-  AB_REQUIRE(what == AB_PREDICT_MEAN || (what == AB_PREDICT_MARGINAL && var != nullptr) ||
-                 (what == AB_PREDICT_JOINT && joint != nullptr),
-             "prediction kind / outputs");
-  Lock lock(h);
-  AB_TRY(require_usable(f));
+} // extern "C"
+
+namespace ab {
+
+// Column chunk [j0, j0 + cb) of diag(K^-1): column sums of squares of L^-1 E_J obtained by a
+// triangular solve that starts at row j0 (rows above are structurally zero).
+static int inverse_diagonal_chunk(ab_handle_s *h, const ab_factor_s *f, int64_t j0, int64_t cb,
+                                  ab_matrix_s *G, double *d_a) {
+  const int64_t rows = f->n - j0; // j0 is a multiple of LEAF
+  AB_TRY(fill(h, view(G), rows, cb, 0.));
+  set_diag_one_kernel<<<static_cast<unsigned>((cb + 255) / 256), 256, 0, h->stream>>>(G->d, G->ld,
+                                                                                      cb);
+  AB_LAUNCHED(h);
+  AB_TRY(trsm_left_lower(h, view(f->m).sub(j0, j0), f->dinv + (j0 / LEAF) * LEAF * LEAF, rows,
+                         view(G), cb));
+  return column_dots(h, view(G), view(G), rows, cb, d_a + j0);
+}
+
+// Shared implementation of ab_gp_cv / ab_dist_gp_cv.  Work is restricted to the groups (or, for
+// pure leave-one-out, the column chunks) c with c % stride == phase; outputs of the other shards
+// are left at zero so that a sum over ranks assembles the full result.  stride == 1: everything,
+// through one explicit inverse factor (N^3/3); stride > 1: per-shard triangular solves.
+int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *information,
+               const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+               int phase, int stride, double *mean, double *var, double *joint, double *score) {
   const int64_t n = f->n;
+  if (score != nullptr) {
+    *score = 0.;
+  }
   if (ngroups == 0 || n == 0) {
-    if (score != nullptr) {
-      *score = 0.;
-    }
     return AB_OK;
   }
   const int64_t total = offsets[ngroups];
@@ -774,41 +690,66 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
     AB_REQUIRE(offsets[g + 1] >= offsets[g], "offsets must be non-decreasing");
     maxg = std::max(maxg, offsets[g + 1] - offsets[g]);
   }
+  const bool sharded = stride > 1;
+  const bool pure_loo = maxg == 1 && total == n && ngroups == n;
   Scope sc(h);
-  timings_reset(h);
   ab_matrix_s *W = nullptr;
-  phase_begin(h, PH_SOLVE);
-  AB_TRY(inverse_factor(h, sc, f, &W));
-  phase_end(h, PH_SOLVE);
+  if (!sharded) {
+    phase_begin(h, PH_SOLVE);
+    AB_TRY(inverse_factor(h, sc, f, &W));
+    phase_end(h, PH_SOLVE);
+  }
 
   void *d_y = nullptr, *d_info = nullptr, *d_idx = nullptr, *d_mean = nullptr, *d_var = nullptr;
-  AB_TRY(upload_bytes(h, sc, y, static_cast<size_t>(n) * sizeof(double), &d_y));
-  AB_TRY(upload_bytes(h, sc, information, static_cast<size_t>(n) * sizeof(double), &d_info));
+  const size_t nbytes = static_cast<size_t>(n) * sizeof(double);
+  AB_TRY(upload_bytes(h, sc, y, nbytes, &d_y));
+  AB_TRY(upload_bytes(h, sc, information, nbytes, &d_info));
   AB_TRY(upload_bytes(h, sc, indices, static_cast<size_t>(total) * sizeof(int64_t), &d_idx));
-  AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_mean));
-  AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_var));
-  AB_CUDA(cudaMemsetAsync(d_mean, 0, static_cast<size_t>(n) * sizeof(double), h->stream));
-  AB_CUDA(cudaMemsetAsync(d_var, 0, static_cast<size_t>(n) * sizeof(double), h->stream));
+  AB_TRY(sc.alloc(nbytes, &d_mean));
+  AB_TRY(sc.alloc(nbytes, &d_var));
+  AB_CUDA(cudaMemsetAsync(d_mean, 0, nbytes, h->stream));
+  AB_CUDA(cudaMemsetAsync(d_var, 0, nbytes, h->stream));
 
   phase_begin(h, PH_PREDICT);
   double total_score = 0.;
-  if (maxg == 1 && total == n && ngroups == n) {
+  if (pure_loo) {
     // pure leave-one-out: everything is element-wise on diag(K^-1)
     void *d_a = nullptr, *d_terms = nullptr;
-    AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_a));
-    AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d_terms));
-    AB_TRY(column_dots(h, view(W), view(W), n, n, static_cast<double *>(d_a)));
-    loo_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, h->stream>>>(
-        static_cast<double *>(d_a), static_cast<double *>(d_y), static_cast<double *>(d_info), n,
-        static_cast<double *>(d_mean), static_cast<double *>(d_var),
-        static_cast<double *>(d_terms));
-    AB_LAUNCHED(h);
+    AB_TRY(sc.alloc(nbytes, &d_a));
+    AB_TRY(sc.alloc(nbytes, &d_terms));
+    AB_CUDA(cudaMemsetAsync(d_terms, 0, nbytes, h->stream));
+    if (!sharded) {
+      AB_TRY(column_dots(h, view(W), view(W), n, n, static_cast<double *>(d_a)));
+      loo_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, h->stream>>>(
+          static_cast<double *>(d_a), static_cast<double *>(d_y), static_cast<double *>(d_info), n,
+          static_cast<double *>(d_mean), static_cast<double *>(d_var),
+          static_cast<double *>(d_terms));
+      AB_LAUNCHED(h);
+    } else {
+      constexpr int64_t CB = 2048; // column chunk dealt cyclically to the ranks
+      ab_matrix_s *G = nullptr;
+      AB_TRY(matrix_new(h, n, std::min(CB, n), &G));
+      sc.own(G);
+      int64_t c = 0;
+      for (int64_t j0 = 0; j0 < n; j0 += CB, ++c) {
+        if (c % stride != phase) {
+          continue;
+        }
+        const int64_t cb = std::min(CB, n - j0);
+        AB_TRY(inverse_diagonal_chunk(h, f, j0, cb, G, static_cast<double *>(d_a)));
+        loo_kernel<<<static_cast<unsigned>((cb + 255) / 256), 256, 0, h->stream>>>(
+            static_cast<double *>(d_a) + j0, static_cast<double *>(d_y) + j0,
+            static_cast<double *>(d_info) + j0, cb, static_cast<double *>(d_mean) + j0,
+            static_cast<double *>(d_var) + j0, static_cast<double *>(d_terms) + j0);
+        AB_LAUNCHED(h);
+      }
+    }
     phase_end(h, PH_PREDICT);
-    AB_TRY(download_bytes(h, d_mean, static_cast<size_t>(n) * sizeof(double), mean));
+    AB_TRY(download_bytes(h, d_mean, nbytes, mean));
     if (what != AB_PREDICT_MEAN) {
       // for 1x1 groups the joint blocks, in key order, are the variances in index order
       std::vector<double> v(n);
-      AB_TRY(download_bytes(h, d_var, static_cast<size_t>(n) * sizeof(double), v.data()));
+      AB_TRY(download_bytes(h, d_var, nbytes, v.data()));
       if (what == AB_PREDICT_MARGINAL) {
         std::copy(v.begin(), v.end(), var);
       } else {
@@ -819,7 +760,7 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
     }
     if (score != nullptr) {
       std::vector<double> t(n);
-      AB_TRY(download_bytes(h, d_terms, static_cast<size_t>(n) * sizeof(double), t.data()));
+      AB_TRY(download_bytes(h, d_terms, nbytes, t.data()));
       for (int64_t g = 0; g < n; ++g) {
         total_score += t[indices[offsets[g]]];
       }
@@ -842,15 +783,16 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
   sc.own(Tg);
   AB_TRY(matrix_new(h, maxg, 2, &x));
   sc.own(x);
-  void *d_diag = nullptr, *d_gscal = nullptr, *d_joint = nullptr;
+  void *d_diag = nullptr, *d_gscal = nullptr;
   AB_TRY(sc.alloc(static_cast<size_t>(maxg) * sizeof(double), &d_diag));
   AB_TRY(sc.alloc(static_cast<size_t>(ngroups) * 2 * sizeof(double), &d_gscal));
+  AB_CUDA(cudaMemsetAsync(d_gscal, 0, static_cast<size_t>(ngroups) * 2 * sizeof(double),
+                          h->stream));
   ab_matrix_s *Cg = nullptr;
   if (what == AB_PREDICT_JOINT) {
     AB_TRY(matrix_new(h, maxg, maxg, &Cg));
     sc.own(Cg);
   }
-  (void)d_joint;
   const int64_t nleaf = (maxg + LEAF - 1) / LEAF;
   void *d_ginv = nullptr;
   AB_TRY(sc.alloc(static_cast<size_t>(nleaf) * LEAF * LEAF * sizeof(double), &d_ginv));
@@ -862,8 +804,15 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
     if (k == 0) {
       continue;
     }
+    if (g % stride != phase) {
+      if (what == AB_PREDICT_JOINT) {
+        std::fill(joint_cursor, joint_cursor + k * k, 0.);
+        joint_cursor += k * k;
+      }
+      continue;
+    }
     const int64_t *gi = static_cast<int64_t *>(d_idx) + offsets[g];
-    AB_TRY(inverse_block_device(h, W, gi, indices + offsets[g], k, G, view(A)));
+    AB_TRY(inverse_block_device(h, f, W, gi, indices + offsets[g], k, G, view(A)));
     AB_TRY(potrf(h, view(A), k, static_cast<double *>(d_ginv), h->d_flags));
     // x = A^-1 v_g  (column 0 of x), keep v_g in column 1 for the score
     gather_vec_kernel<<<static_cast<unsigned>((k + 255) / 256), 256, 0, h->stream>>>(
@@ -900,9 +849,9 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
     }
   }
   phase_end(h, PH_PREDICT);
-  AB_TRY(download_bytes(h, d_mean, static_cast<size_t>(n) * sizeof(double), mean));
+  AB_TRY(download_bytes(h, d_mean, nbytes, mean));
   if (what == AB_PREDICT_MARGINAL) {
-    AB_TRY(download_bytes(h, d_var, static_cast<size_t>(n) * sizeof(double), var));
+    AB_TRY(download_bytes(h, d_var, nbytes, var));
   }
   AB_TRY(download_bytes(h, h->d_flags, sizeof(int), h->h_flags));
   if (h->h_flags[0] != INT_MAX) {
@@ -914,7 +863,7 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
     AB_TRY(download_bytes(h, d_gscal, gs.size() * sizeof(double), gs.data()));
     for (int64_t g = 0; g < ngroups; ++g) {
       const int64_t k = offsets[g + 1] - offsets[g];
-      if (k == 0) {
+      if (k == 0 || g % stride != phase) {
         continue;
       }
       total_score += 0.5 * (-gs[2 * g] + gs[2 * g + 1] + static_cast<double>(k) * std::log(2 * M_PI));
@@ -923,6 +872,48 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
   }
   cudaEventRecord(h->ev_total_end, h->stream);
   return AB_OK;
+}
+
+} // namespace ab
+
+extern "C" {
+
+int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *information,
+             const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+             double *mean, double *var, double *joint, double *score) {
+  AB_REQUIRE(h != nullptr && y != nullptr && information != nullptr && indices != nullptr &&
+                 offsets != nullptr && mean != nullptr && ngroups >= 0,
+             "null");
+  AB_REQUIRE(what == AB_PREDICT_MEAN || (what == AB_PREDICT_MARGINAL && var != nullptr) ||
+                 (what == AB_PREDICT_JOINT && joint != nullptr),
+             "prediction kind / outputs");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  timings_reset(h);
+  return gp_cv_impl(h, f, y, information, indices, offsets, ngroups, what, 0, 1, mean, var, joint,
+                    score);
+}
+
+int ab_gp_cv_shard(ab_handle h, ab_factor f, const double *y, const double *information,
+                   const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+                   int shard, int nshards, double *mean, double *var, double *score) {
+  AB_REQUIRE(h != nullptr && y != nullptr && information != nullptr && indices != nullptr &&
+                 offsets != nullptr && mean != nullptr && ngroups >= 0,
+             "null");
+  AB_REQUIRE(what == AB_PREDICT_MEAN || (what == AB_PREDICT_MARGINAL && var != nullptr),
+             "sharded CV returns means or marginals");
+  AB_REQUIRE(nshards >= 1 && shard >= 0 && shard < nshards, "shard / nshards");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  timings_reset(h);
+  // nshards == 1 still takes the per-shard solve path (stride 2 with every unit in phase 0 would
+  // change the partition), so run it as "stride = nshards" with a guard for the degenerate case
+  if (nshards == 1) {
+    return gp_cv_impl(h, f, y, information, indices, offsets, ngroups, what, 0, 1, mean, var,
+                      nullptr, score);
+  }
+  return gp_cv_impl(h, f, y, information, indices, offsets, ngroups, what, shard, nshards, mean,
+                    var, nullptr, score);
 }
 
 // ---- dense building block ---------------------------------------------------------------------

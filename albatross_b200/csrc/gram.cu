@@ -537,6 +537,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
     }
   }
   const bool mirror = SYM && I != J && !(flags & AB_GRAM_LOWER_ONLY);
+  const bool unaligned = flags & GRAM_UNALIGNED; // output sub-view that is only 8-byte aligned
   const int64_t gi = i0 + r0;
 
 #pragma unroll 1
@@ -608,10 +609,13 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
       const int64_t gj = j0 + cbase + k;
       if (gj < m) {
         double *dst = out + gi + gj * ld;
-        if (gi + 1 < n) {
+        if (gi + 1 < n && !unaligned) {
           *reinterpret_cast<double2 *>(dst) = make_double2(vals[2 * k], vals[2 * k + 1]);
         } else if (gi < n) {
           dst[0] = vals[2 * k];
+          if (gi + 1 < n) {
+            dst[1] = vals[2 * k + 1];
+          }
         }
       }
     }
@@ -687,6 +691,9 @@ static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *
   AB_REQUIRE(tiles < (int64_t(1) << 31), "Gram too large for one launch");
   const dim3 grid(static_cast<unsigned>(tiles));
   const dim3 block(GRAM_THREADS);
+  if (reinterpret_cast<uintptr_t>(out) % 16 != 0 || ld % 2 != 0) {
+    flags |= GRAM_UNALIGNED;
+  }
   // pick the leanest kernel specialisation the program allows
   int mode = MODE_STACK;
   if (P.mode == 0) {
@@ -734,6 +741,27 @@ static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *
 #undef AB_GRAM_CASE
   AB_LAUNCHED(h);
   return AB_OK;
+}
+
+int gram_into(ab_handle_s *h, const DevProg &P, int dim, bool sym, const double *fx, int64_t ldfx,
+              int64_t n, const double *fy, int64_t ldfy, int64_t m, double *out, int64_t ld,
+              uint32_t flags) {
+  if (sym) {
+    return launch_gram<true>(h, P, dim, fx, ldfx, n, fx, ldfx, n, out, ld, flags);
+  }
+  return launch_gram<false>(h, P, dim, fx, ldfx, n, fy, ldfy, m, out, ld, 0u);
+}
+
+int gram_diag_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *feats, double *d_out);
+
+int gram_diag_into(ab_handle_s *h, const DevProg &P, int dim, const double *f, int64_t ldf,
+                   int64_t n, double *d_out) {
+  ab_matrix_s view;
+  view.d = const_cast<double *>(f);
+  view.rows = dim;
+  view.cols = n;
+  view.ld = ldf;
+  return gram_diag_device(h, P, &view, d_out);
 }
 
 int gram_sym_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *feats, uint32_t flags,

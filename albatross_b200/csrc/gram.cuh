@@ -50,4 +50,15 @@ struct DevProg {
 
 int compile_program(const ab_op *prog, int nops, DevProg *out);
 
+constexpr uint32_t GRAM_UNALIGNED = 0x100u; // internal flag: scalar stores (set by the launcher)
+
+// Gram blocks written into an existing device buffer (possibly a sub-view of a larger matrix).
+// Features: point i at f[i * ldf .. i * ldf + dim).  sym: lower triangle (+ mirror unless
+// AB_GRAM_LOWER_ONLY) of k(fx, fx); otherwise the n x m cross block k(fx, fy).
+int gram_into(ab_handle_s *h, const DevProg &P, int dim, bool sym, const double *fx, int64_t ldfx,
+              int64_t n, const double *fy, int64_t ldfy, int64_t m, double *out, int64_t ld,
+              uint32_t flags);
+int gram_diag_into(ab_handle_s *h, const DevProg &P, int dim, const double *f, int64_t ldf,
+                   int64_t n, double *d_out);
+
 } // namespace ab

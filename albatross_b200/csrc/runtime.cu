@@ -215,6 +215,7 @@ int ab_destroy(ab_handle h) {
   if (h == nullptr) {
     return AB_OK;
   }
+  ab_dist_finalize(h);
   ab_trim(h);
   for (int p = 0; p < PH_COUNT; ++p) {
     cudaEventDestroy(h->ev_begin[p]);

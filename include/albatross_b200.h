@@ -240,11 +240,112 @@ AB_API int ab_gp_cv(ab_handle h, ab_factor factor, const double *y, const double
              const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
              double *mean, double *var, double *joint, double *score);
 
+/*
+ * One shard of ab_gp_cv: only the groups g with g % nshards == shard (for pure leave-one-out: the
+ * 2048-column chunks c of the inverse diagonal with c % nshards == shard) are processed, through
+ * per-shard triangular solves instead of one explicit inverse factor; entries of other shards are
+ * returned as zero, so that the element-wise SUM over shards is the full ab_gp_cv result.  This is
+ * the unit of work ab_dist_gp_cv gives each rank; a single process driving several handles can use
+ * it directly.
+ */
+AB_API int ab_gp_cv_shard(ab_handle h, ab_factor factor, const double *y, const double *information,
+                   const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+                   int shard, int nshards, double *mean, double *var, double *score);
+
 /* Device-resident variants (inputs already in HBM; results stay in HBM unless a host ptr is given). */
 AB_API int ab_gp_fit_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
                 ab_matrix yvar, ab_factor *factor, ab_matrix *information);
 AB_API int ab_gp_nll_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
                 double *nll);
+
+/* ---- sparse GP (src/models/sparse_gp.hpp) --------------------------------------------------- */
+
+typedef struct ab_sparse_fit_s *ab_sparse; /* device-resident Fit<SparseGPFit>: u, K_uu factor, R, v */
+
+/*
+ * SparseGaussianProcessRegression::_fit_impl sparse_gp.hpp:381-404 (compute_internal_components
+ * :632-706 + compute_sigma_qr :368-375) for the FITC / PITC approximation.
+ *   feats/y/yvar     n observations (yvar may be NULL = zero measurement variance);
+ *   inducing         m inducing features (the caller runs its InducingPointStrategy, e.g.
+ *                    UniformlySpacedInducingPoints sparse_gp.hpp:34-47, on the host);
+ *   indices/offsets  the GroupIndexer of group_by(features, grouper).indexers() as CSR in std::map
+ *                    key order (ab_group_indexers): observations are reordered by it (:649-668).
+ *                    LeaveOneOutGrouper (all groups singletons) = FITC;
+ *   nuggets          measurement / inducing nugget (defaults 1e-8, sparse_gp.hpp:20-26, :281-287).
+ * information (m doubles, optional) = v of :396-398; log_likelihood (optional) = the data term of
+ * log_likelihood() :539-603 for the same inputs (the prior term is a host scalar of the caller).
+ * QR of B is taken as CholQR2 of the better-conditioned C = B L_u^-T (see sparse.cu); R and the
+ * column permutation are representation-internal; ab_sparse_export_R returns an R with R^T R = B^T B.
+ * When the handle is part of a distributed group (ab_dist_init) each rank passes ITS shard of the
+ * observations/groups; the m x m Gram products and the scalars are all-reduced, the resulting fit
+ * is replicated on every rank.
+ */
+AB_API int ab_sparse_fit(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n,
+                  int dim, const double *y, const double *yvar, const double *inducing, int64_t m,
+                  const int64_t *indices, const int64_t *offsets, int64_t ngroups,
+                  double measurement_nugget, double inducing_nugget, ab_sparse *out,
+                  double *information, double *log_likelihood);
+AB_API int ab_sparse_free(ab_handle h, ab_sparse f);
+AB_API int ab_sparse_info(ab_sparse f, int64_t *m, double *log_likelihood);
+/* model.log_likelihood(dataset) for the sparse model (:539-603): a fresh fit, only the scalar kept. */
+AB_API int ab_sparse_log_likelihood(ab_handle h, const ab_op *prog, int nops, const double *feats,
+                             int64_t n, int dim, const double *y, const double *yvar,
+                             const double *inducing, int64_t m, const int64_t *indices,
+                             const int64_t *offsets, int64_t ngroups, double measurement_nugget,
+                             double inducing_nugget, double *log_likelihood);
+/* _predict_impl x3 sparse_gp.hpp:468-536; outputs as ab_gp_predict. */
+AB_API int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
+                      const double *test_feats, int64_t p, int what, double *mean, double *var,
+                      double *cov);
+/* sigma_R (m x m upper triangular, column-major, get_R linalg/qr_utils.hpp:18-27) with P = I. */
+AB_API int ab_sparse_export_R(ab_handle h, ab_sparse f, double *R);
+
+/* ---- one process per GPU: distributed group (NCCL over NVLink / NVSwitch) -------------------- */
+
+#define AB_DIST_ID_BYTES 128
+/*
+ * Rank 0 creates an id (ncclGetUniqueId) and hands the bytes to the other ranks by whatever the
+ * launcher offers (torch.distributed broadcast, MPI, a file); every rank then calls ab_dist_init.
+ * libnccl.so.2 is loaded on first use (dlopen); single-GPU users never need it.
+ */
+AB_API int ab_dist_unique_id(void *id_out);
+AB_API int ab_dist_init(ab_handle h, int rank, int world, const void *id);
+AB_API int ab_dist_finalize(ab_handle h);
+AB_API int ab_dist_info(ab_handle h, int *rank, int *world);
+
+typedef struct ab_dist_factor_s *ab_dist_factor; /* block-column-cyclic factor, one shard per rank */
+
+/*
+ * Distributed model.fit(dataset) for matrices that outgrow one GPU (BASELINE configs[2],
+ * N = 131 072): the Gram matrix is generated directly in block-column-cyclic layout (block size
+ * `nb`, block column j on rank j % world; every rank holds all features), factorised by a
+ * right-looking blocked Cholesky with one NCCL panel broadcast per block column (look-ahead 1,
+ * overlapped with the trailing DSYRK/DGEMM update), and the information vector K^-1 y is computed by
+ * pipelined block substitutions.  All ranks call with identical arguments; information (n doubles,
+ * optional) and nll (optional; 0.5 (log|K| + y^T K^-1 y + n log 2 pi), likelihood.hpp:38-47) are
+ * returned on every rank.  yvar as in ab_gp_fit.  nb = 0 picks the default.
+ */
+AB_API int ab_dist_gp_fit(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n,
+                   int dim, const double *y, const double *yvar, int64_t nb, ab_dist_factor *factor,
+                   double *information, double *nll);
+AB_API int ab_dist_factor_free(ab_handle h, ab_dist_factor f);
+/* Owner rank of block column j and its local index: the integer contract of the layout. */
+AB_API int ab_dist_block_owner(int64_t block, int world, int *rank, int64_t *local_block);
+/*
+ * Gram row-block sharding: rank r builds rows [row0, row0 + rows) x all columns of
+ * the symmetric Gram; the split balances rows.  Returns the local shard as an ab_matrix (rows x n).
+ */
+AB_API int ab_dist_gram_rows(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n,
+                      int dim, int64_t *row0, int64_t *rows, ab_matrix *out);
+/*
+ * Leave-one-group-out CV with folds sharded over ranks: every rank holds the same
+ * single-GPU factor (N <= 65 536 fits one GPU); rank r processes groups g with g % world == r and
+ * the per-observation results are all-reduced.  Outputs as ab_gp_cv (joint blocks are returned only
+ * for the caller's own groups, others zero-filled).
+ */
+AB_API int ab_dist_gp_cv(ab_handle h, ab_factor factor, const double *y, const double *information,
+                  const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+                  double *mean, double *var, double *score);
 
 /* ---- dense building block -------------------------------------------------------------------- */
 

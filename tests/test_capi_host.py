@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "albatross_b200.h")).read()
-    return sorted(set(re.findall(r"AB_API[^;(]*?\b(ab_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"AB_API[^;(]*?\b(ab_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
