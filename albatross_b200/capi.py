@@ -332,6 +332,12 @@ class Handle:
                                    C.byref(out)))
         return Matrix(self, out)
 
+    def gram_cross_d(self, ops, params, fx_dev, fy_dev):
+        prog, nops = program(ops, params)
+        out = C.c_void_p()
+        _check(lib().ab_gram_cross_d(self.ptr, prog, nops, fx_dev.ptr, fy_dev.ptr, C.byref(out)))
+        return Matrix(self, out)
+
     def gram_cross(self, ops, params, fx, fy):
         prog, nops = program(ops, params)
         x, y = _feats(fx), _feats(fy)

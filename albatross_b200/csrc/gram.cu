@@ -11,7 +11,7 @@
 // <= 64 FP64-pipe instructions per pair.  libdevice exp()/sqrt() alone cost ~21/17 each, so the
 // evaluator uses its own exp (128-entry 2^(j/128) table in shared memory + degree-5 polynomial,
 // 10 FP64 ops, <= 1 ulp) and sqrt (MUFU.RSQ64H seed + Goldschmidt, 7 FP64 ops, <= 1 ulp).
-#include "gram.cuh"
+#include "gram_kernel.cuh"
 
 #include <cmath>
 
@@ -153,299 +153,8 @@ int compile_program(const ab_op *prog, int nops, DevProg *out) {
 // device: lean fp64 exp / sqrt
 // ------------------------------------------------------------------------------------------------
 
-// 2^(j/128), j = 0..127, correctly rounded.
-__device__ const double EXP_TABLE[128] = {
-    0x1.0000000000000p+0,
-    0x1.0163da9fb3335p+0,
-    0x1.02c9a3e778061p+0,
-    0x1.04315e86e7f85p+0,
-    0x1.059b0d3158574p+0,
-    0x1.0706b29ddf6dep+0,
-    0x1.0874518759bc8p+0,
-    0x1.09e3ecac6f383p+0,
-    0x1.0b5586cf9890fp+0,
-    0x1.0cc922b7247f7p+0,
-    0x1.0e3ec32d3d1a2p+0,
-    0x1.0fb66affed31bp+0,
-    0x1.11301d0125b51p+0,
-    0x1.12abdc06c31ccp+0,
-    0x1.1429aaea92de0p+0,
-    0x1.15a98c8a58e51p+0,
-    0x1.172b83c7d517bp+0,
-    0x1.18af9388c8deap+0,
-    0x1.1a35beb6fcb75p+0,
-    0x1.1bbe084045cd4p+0,
-    0x1.1d4873168b9aap+0,
-    0x1.1ed5022fcd91dp+0,
-    0x1.2063b88628cd6p+0,
-    0x1.21f49917ddc96p+0,
-    0x1.2387a6e756238p+0,
-    0x1.251ce4fb2a63fp+0,
-    0x1.26b4565e27cddp+0,
-    0x1.284dfe1f56381p+0,
-    0x1.29e9df51fdee1p+0,
-    0x1.2b87fd0dad990p+0,
-    0x1.2d285a6e4030bp+0,
-    0x1.2ecafa93e2f56p+0,
-    0x1.306fe0a31b715p+0,
-    0x1.32170fc4cd831p+0,
-    0x1.33c08b26416ffp+0,
-    0x1.356c55f929ff1p+0,
-    0x1.371a7373aa9cbp+0,
-    0x1.38cae6d05d866p+0,
-    0x1.3a7db34e59ff7p+0,
-    0x1.3c32dc313a8e5p+0,
-    0x1.3dea64c123422p+0,
-    0x1.3fa4504ac801cp+0,
-    0x1.4160a21f72e2ap+0,
-    0x1.431f5d950a897p+0,
-    0x1.44e086061892dp+0,
-    0x1.46a41ed1d0057p+0,
-    0x1.486a2b5c13cd0p+0,
-    0x1.4a32af0d7d3dep+0,
-    0x1.4bfdad5362a27p+0,
-    0x1.4dcb299fddd0dp+0,
-    0x1.4f9b2769d2ca7p+0,
-    0x1.516daa2cf6642p+0,
-    0x1.5342b569d4f82p+0,
-    0x1.551a4ca5d920fp+0,
-    0x1.56f4736b527dap+0,
-    0x1.58d12d497c7fdp+0,
-    0x1.5ab07dd485429p+0,
-    0x1.5c9268a5946b7p+0,
-    0x1.5e76f15ad2148p+0,
-    0x1.605e1b976dc09p+0,
-    0x1.6247eb03a5585p+0,
-    0x1.6434634ccc320p+0,
-    0x1.6623882552225p+0,
-    0x1.68155d44ca973p+0,
-    0x1.6a09e667f3bcdp+0,
-    0x1.6c012750bdabfp+0,
-    0x1.6dfb23c651a2fp+0,
-    0x1.6ff7df9519484p+0,
-    0x1.71f75e8ec5f74p+0,
-    0x1.73f9a48a58174p+0,
-    0x1.75feb564267c9p+0,
-    0x1.780694fde5d3fp+0,
-    0x1.7a11473eb0187p+0,
-    0x1.7c1ed0130c132p+0,
-    0x1.7e2f336cf4e62p+0,
-    0x1.80427543e1a12p+0,
-    0x1.82589994cce13p+0,
-    0x1.8471a4623c7adp+0,
-    0x1.868d99b4492edp+0,
-    0x1.88ac7d98a6699p+0,
-    0x1.8ace5422aa0dbp+0,
-    0x1.8cf3216b5448cp+0,
-    0x1.8f1ae99157736p+0,
-    0x1.9145b0b91ffc6p+0,
-    0x1.93737b0cdc5e5p+0,
-    0x1.95a44cbc8520fp+0,
-    0x1.97d829fde4e50p+0,
-    0x1.9a0f170ca07bap+0,
-    0x1.9c49182a3f090p+0,
-    0x1.9e86319e32323p+0,
-    0x1.a0c667b5de565p+0,
-    0x1.a309bec4a2d33p+0,
-    0x1.a5503b23e255dp+0,
-    0x1.a799e1330b358p+0,
-    0x1.a9e6b5579fdbfp+0,
-    0x1.ac36bbfd3f37ap+0,
-    0x1.ae89f995ad3adp+0,
-    0x1.b0e07298db666p+0,
-    0x1.b33a2b84f15fbp+0,
-    0x1.b59728de5593ap+0,
-    0x1.b7f76f2fb5e47p+0,
-    0x1.ba5b030a1064ap+0,
-    0x1.bcc1e904bc1d2p+0,
-    0x1.bf2c25bd71e09p+0,
-    0x1.c199bdd85529cp+0,
-    0x1.c40ab5fffd07ap+0,
-    0x1.c67f12e57d14bp+0,
-    0x1.c8f6d9406e7b5p+0,
-    0x1.cb720dcef9069p+0,
-    0x1.cdf0b555dc3fap+0,
-    0x1.d072d4a07897cp+0,
-    0x1.d2f87080d89f2p+0,
-    0x1.d5818dcfba487p+0,
-    0x1.d80e316c98398p+0,
-    0x1.da9e603db3285p+0,
-    0x1.dd321f301b460p+0,
-    0x1.dfc97337b9b5fp+0,
-    0x1.e264614f5a129p+0,
-    0x1.e502ee78b3ff6p+0,
-    0x1.e7a51fbc74c83p+0,
-    0x1.ea4afa2a490dap+0,
-    0x1.ecf482d8e67f1p+0,
-    0x1.efa1bee615a27p+0,
-    0x1.f252b376bba97p+0,
-    0x1.f50765b6e4540p+0,
-    0x1.f7bfdad9cbe14p+0,
-    0x1.fa7c1819e90d8p+0,
-    0x1.fd3c22b8f71f1p+0};
 
 
-// exp(x) for x <= 0 (the argument of every radial kernel).  x = 128 n ln2/128 + j ln2/128 + r,
-// exp(x) = 2^n * T[j] * (1 + r + ... + r^5/120), |r| <= ln2/256.  10 FP64-pipe instructions; the table
-// lookup, the index arithmetic and the 2^n scaling run on the LSU / integer pipes.  Valid for
-// -708 <= x <= -0; `bad` accumulates (sign bit set) when x is outside that range so that the caller
-// can patch the rare cases: x < -708 is flushed to 0 (the reference would return a subnormal
-// < 3e-308 there), NaN stays NaN.
-__device__ __forceinline__ double exp_nonpos(double x, const double *__restrict__ tab, int &bad) {
-  const double t = fma(x, 184.6649652337873, 6755399441055744.0); // x * 128/ln2, round to nearest
-  const int m = __double2loint(t);
-  const double mf = t - 6755399441055744.0;
-  double r = fma(mf, -0x1.62e42fef00000p-8, x);  // ln2/128 high part (32 significant bits)
-  r = fma(mf, -0x1.473de6af278edp-41, r);        // ln2/128 low part
-  double p = fma(r, 0.008333333333333333, 0.041666666666666664);
-  p = fma(p, r, 0.16666666666666666);
-  p = fma(p, r, 0.5);
-  const double r2 = r * r;
-  const double q = fma(p, r2, r); // expm1(r)
-  const double tj = tab[m & 127];
-  const double res = fma(tj, q, tj);
-  // in range  <=>  hi(x) in [0x80000000, 0xC0862000]  (-0 .. -708)
-  bad |= 0x40862000 - (__double2hiint(x) ^ 0x80000000);
-  return __hiloint2double(__double2hiint(res) + ((m >> 7) << 20), __double2loint(res));
-}
-
-// sqrt(a) for positive normal a: MUFU.RSQ64H seed (2^-22) + one Goldschmidt step + one residual
-// correction (7 FP64-pipe instructions, <= 1 ulp).  `bad` gets its sign bit set for zero,
-// subnormal, infinite, NaN or negative arguments, which the caller patches inline.
-__device__ __forceinline__ double sqrt_fast(double a, int &bad) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double g = a * y;
-  double h = 0.5 * y;
-  const double r = fma(-h, g, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  const double e = fma(-g, g, a);
-  // positive normal  <=>  hi(a) in [0x00100000, 0x7fefffff]
-  const int hi = __double2hiint(a);
-  bad |= (hi - 0x00100000) | (0x7fefffff - hi);
-  return fma(e, h, g);
-}
-
-// ------------------------------------------------------------------------------------------------
-// device: covariance program evaluation
-// ------------------------------------------------------------------------------------------------
-
-// Kernel specialisations (template parameter MODE): which parts of the generic evaluator exist.
-//   0  sum of single radial/constant leaves (e.g. SE + Matern52)            - no equality, no products
-//   1  ... plus IndependentNoise leaves (e.g. SE + noise)                   - feature equality needed
-//   2  general sum of products                                              - `prod` accumulator
-//   3  arbitrary nesting: postfix evaluation with a stack (slow path)
-constexpr int MODE_SUM = 0, MODE_SUM_NOISE = 1, MODE_SOP = 2, MODE_STACK = 3;
-
-// Sum-of-products evaluation of NP pairs at once: the op loop is uniform across the CTA and its
-// decode cost is amortised over the NP pairs a thread owns.  Single-leaf terms (the common case)
-// accumulate straight into `out` with one FMA; `prod` only exists for genuine products.
-template <int NP, int MODE>
-__device__ __forceinline__ void eval_sop(const DevProg &P, const double (&d2)[NP],
-                                         const double (&dist)[NP], unsigned eqmask,
-                                         const double *__restrict__ tab, double (&out)[NP]) {
-  double prod[MODE >= MODE_SOP ? NP : 1];
-#pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    out[i] = 0.;
-  }
-  for (int k = 0; k < P.nops; ++k) {
-    const int kind = P.ops[k].kind;
-    const int flags = P.ops[k].flags;
-    const double amp = P.ops[k].amp;
-    double v[NP];
-    if (kind == DK_RADIAL) {
-      if (flags & DF_USES_DIST) {
-        const double a1 = P.ops[k].a1;
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          v[i] = a1 * dist[i];
-        }
-      } else {
-        const double a2 = P.ops[k].a2;
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          v[i] = a2 * d2[i];
-        }
-      }
-      int bad = 0;
-      double e[NP];
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        e[i] = exp_nonpos(v[i], tab, bad);
-      }
-      if (bad < 0) { // rare: some argument outside [-708, -0]: underflow -> 0, NaN -> NaN
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          e[i] = (v[i] < -708.0) ? 0. : ((v[i] != v[i]) ? v[i] : e[i]);
-        }
-      }
-      if (flags & DF_POLY_D1) {
-        const double b1 = P.ops[k].b1;
-        if (flags & DF_POLY_D2) {
-          const double b2 = P.ops[k].b2;
-#pragma unroll
-          for (int i = 0; i < NP; ++i) {
-            v[i] = e[i] * fma(b2, d2[i], fma(b1, dist[i], 1.));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < NP; ++i) {
-            v[i] = e[i] * fma(b1, dist[i], 1.);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          v[i] = e[i];
-        }
-      }
-    } else if (MODE >= MODE_SUM_NOISE && kind == DK_NOISE) {
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        v[i] = ((eqmask >> i) & 1u) ? 1. : 0.;
-      }
-    } else {
-      const double c = kind == DK_CONST ? 1. : 0.;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        v[i] = c;
-      }
-    }
-    if (MODE < MODE_SOP ||
-        (flags & (DF_TERM_START | DF_TERM_END)) == (DF_TERM_START | DF_TERM_END)) {
-      // single-leaf term: out += amp * v  (out starts at +0, so the first term is exact)
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        out[i] = fma(amp, v[i], out[i]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        v[i] *= amp;
-      }
-      if (!(flags & DF_TERM_START)) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          const double pr = prod[MODE >= MODE_SOP ? i : 0];
-          v[i] = (pr != 0.) ? pr * v[i] : pr; // covariance_function.hpp:362-366
-        }
-      }
-      if (flags & DF_TERM_END) {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          out[i] += v[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          prod[MODE >= MODE_SOP ? i : 0] = v[i];
-        }
-      }
-    }
-  }
-}
 
 __device__ __noinline__ double eval_stack(const DevProg &P, double d2, double dist, bool equal) {
   double stack[8];
@@ -476,179 +185,6 @@ __device__ __noinline__ double eval_stack(const DevProg &P, double d2, double di
     }
   }
   return stack[0];
-}
-
-constexpr int TILE = 64;
-constexpr int LDT = TILE + 1;
-constexpr int GRAM_THREADS = 256;
-constexpr int NPAIR = 8; // 2 rows x 4 columns per thread and pass; 2 passes cover the 64 columns
-
-// SYM: blockIdx.x enumerates tiles (I >= J) of the lower triangle; otherwise I = b % tiles_i.
-template <int DIM, bool SYM, int MODE>
-__global__ void __launch_bounds__(GRAM_THREADS, 2)
-gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, int64_t ldfx,
-            int64_t n, const double *__restrict__ fy, int64_t ldfy, int64_t m,
-            double *__restrict__ out, int64_t ld, int tiles_i, uint32_t flags) {
-  __shared__ double tab[128];
-  __shared__ double xs[TILE * DIM];
-  __shared__ double ys[TILE * DIM];
-  __shared__ double stage[SYM ? TILE * LDT : 1];
-
-  int64_t I, J;
-  if (SYM) {
-    const int64_t t = blockIdx.x;
-    int64_t i = static_cast<int64_t>((sqrt(8. * static_cast<double>(t) + 1.) - 1.) * 0.5);
-    while (i * (i + 1) / 2 > t) {
-      --i;
-    }
-    while ((i + 1) * (i + 2) / 2 <= t) {
-      ++i;
-    }
-    I = i;
-    J = t - i * (i + 1) / 2;
-  } else {
-    I = blockIdx.x % tiles_i;
-    J = blockIdx.x / tiles_i;
-  }
-  const int64_t i0 = I * TILE;
-  const int64_t j0 = J * TILE;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-
-  if (tid < 128) {
-    tab[tid] = EXP_TABLE[tid];
-  }
-  for (int idx = tid; idx < TILE * DIM; idx += GRAM_THREADS) {
-    const int p = idx / DIM;
-    const int d = idx - p * DIM;
-    xs[idx] = i0 + p < n ? fx[(i0 + p) * ldfx + d] : 0.;
-    ys[idx] = j0 + p < m ? fy[(j0 + p) * ldfy + d] : 0.;
-  }
-  __syncthreads();
-
-  const int r0 = 2 * lane;
-  double xi[2][DIM];
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-      xi[a][d] = xs[(r0 + a) * DIM + d];
-    }
-  }
-  const bool mirror = SYM && I != J && !(flags & AB_GRAM_LOWER_ONLY);
-  const bool unaligned = flags & GRAM_UNALIGNED; // output sub-view that is only 8-byte aligned
-  const int64_t gi = i0 + r0;
-
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int cbase = pass * 32 + warp * 4;
-    double d2[NPAIR], dist[NPAIR], vals[NPAIR];
-    unsigned eqmask = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = cbase + k;
-      double yj[DIM];
-#pragma unroll
-      for (int d = 0; d < DIM; ++d) {
-        yj[d] = ys[c * DIM + d];
-      }
-#pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        double s = 0.;
-#pragma unroll
-        for (int d = 0; d < DIM; ++d) {
-          const double diff = xi[a][d] - yj[d];
-          s = fma(diff, diff, s);
-        }
-        d2[2 * k + a] = s;
-        dist[2 * k + a] = DIM == 1 ? fabs(xi[a][0] - yj[0]) : 0.;
-        if (MODE != MODE_SUM) {
-          bool eq = true;
-#pragma unroll
-          for (int d = 0; d < DIM; ++d) {
-            eq = eq && (xi[a][d] == yj[d]);
-          }
-          eqmask |= (eq ? 1u : 0u) << (2 * k + a);
-        }
-      }
-    }
-    if (DIM != 1 && P.need_dist) {
-      int bad = 0;
-#pragma unroll
-      for (int i = 0; i < NPAIR; ++i) {
-        dist[i] = sqrt_fast(d2[i], bad);
-      }
-      if (bad < 0) { // rare: a zero / subnormal / non-finite squared distance (e.g. the diagonal)
-#pragma unroll
-        for (int i = 0; i < NPAIR; ++i) {
-          const double a = d2[i];
-          if (!(a >= 2.2250738585072014e-308 && a < INFINITY)) {
-            int ignored = 0;
-            // 0, inf, NaN map to themselves; subnormals are rescaled by 2^108 first
-            dist[i] = (a > 0. && a < INFINITY)
-                          ? sqrt_fast(a * 3.2451855365842673e32, ignored) * 5.551115123125783e-17
-                          : a;
-          }
-        }
-      }
-    }
-
-    if (MODE != MODE_STACK) {
-      eval_sop<NPAIR, MODE>(P, d2, dist, eqmask, tab, vals);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NPAIR; ++i) {
-        vals[i] = eval_stack(P, d2[i], dist[i], (eqmask >> i) & 1u);
-      }
-    }
-
-    // direct tile: rows i0 + r0 (+1), columns j0 + c; 16-byte stores, 512 contiguous bytes per warp.
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t gj = j0 + cbase + k;
-      if (gj < m) {
-        double *dst = out + gi + gj * ld;
-        if (gi + 1 < n && !unaligned) {
-          *reinterpret_cast<double2 *>(dst) = make_double2(vals[2 * k], vals[2 * k + 1]);
-        } else if (gi < n) {
-          dst[0] = vals[2 * k];
-          if (gi + 1 < n) {
-            dst[1] = vals[2 * k + 1];
-          }
-        }
-      }
-    }
-    if (mirror) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = cbase + k;
-        stage[c * LDT + r0] = vals[2 * k];
-        stage[c * LDT + r0 + 1] = vals[2 * k + 1];
-      }
-    }
-  }
-
-  if (mirror) {
-    // transposed tile through shared memory: element (row = j0 + c, col = i0 + r) = stage[c][r];
-    // each warp-store covers 32 consecutive rows (256 contiguous bytes).
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int r = warp * 8 + k;
-      const int64_t gcol = i0 + r;
-      if (gcol < n) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int c = lane + 32 * half;
-          const int64_t grow = j0 + c;
-          if (grow < n) {
-            out[grow + gcol * ld] = stage[c * LDT + r];
-          }
-        }
-      }
-    }
-  }
 }
 
 template <int DIM>
@@ -687,10 +223,8 @@ static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *
   }
   const int64_t ti = (n + TILE - 1) / TILE;
   const int64_t tj = (m + TILE - 1) / TILE;
-  const int64_t tiles = SYM ? ti * (ti + 1) / 2 : ti * tj;
+  const int64_t tiles = gram_items(SYM, ti, tj); // work items (tiles, plus skipped ones for SYM)
   AB_REQUIRE(tiles < (int64_t(1) << 31), "Gram too large for one launch");
-  const dim3 grid(static_cast<unsigned>(tiles));
-  const dim3 block(GRAM_THREADS);
   if (reinterpret_cast<uintptr_t>(out) % 16 != 0 || ld % 2 != 0) {
     flags |= GRAM_UNALIGNED;
   }
@@ -704,27 +238,31 @@ static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *
       }
     }
   }
+  const unsigned ntiles = static_cast<unsigned>(tiles);
+  if (launch_gram_fixed(h, P, dim, SYM, fx, ldfx, n, fy, ldfy, m, out, ld, static_cast<int>(ti),
+                        ntiles, flags)) {
+    AB_LAUNCHED(h);
+    return AB_OK;
+  }
+#define AB_GRAM_ARGS h, P, fx, ldfx, n, fy, ldfy, m, out, ld, static_cast<int>(ti), ntiles, flags
 #define AB_GRAM_CASE(D)                                                                        \
   case D:                                                                                      \
     switch (mode) {                                                                            \
     case MODE_SUM:                                                                             \
-      gram_kernel<D, SYM, MODE_SUM><<<grid, block, 0, h->stream>>>(                            \
-          P, fx, ldfx, n, fy, ldfy, m, out, ld, static_cast<int>(ti), flags);                  \
+      launch_err = gram_launch<D, SYM, EvalProgram<MODE_SUM>>(AB_GRAM_ARGS);                   \
       break;                                                                                   \
     case MODE_SUM_NOISE:                                                                       \
-      gram_kernel<D, SYM, MODE_SUM_NOISE><<<grid, block, 0, h->stream>>>(                      \
-          P, fx, ldfx, n, fy, ldfy, m, out, ld, static_cast<int>(ti), flags);                  \
+      launch_err = gram_launch<D, SYM, EvalProgram<MODE_SUM_NOISE>>(AB_GRAM_ARGS);             \
       break;                                                                                   \
     case MODE_SOP:                                                                             \
-      gram_kernel<D, SYM, MODE_SOP><<<grid, block, 0, h->stream>>>(                            \
-          P, fx, ldfx, n, fy, ldfy, m, out, ld, static_cast<int>(ti), flags);                  \
+      launch_err = gram_launch<D, SYM, EvalProgram<MODE_SOP>>(AB_GRAM_ARGS);                   \
       break;                                                                                   \
     default:                                                                                   \
-      gram_kernel<D, SYM, MODE_STACK><<<grid, block, 0, h->stream>>>(                          \
-          P, fx, ldfx, n, fy, ldfy, m, out, ld, static_cast<int>(ti), flags);                  \
+      launch_err = gram_launch<D, SYM, EvalProgram<MODE_STACK>>(AB_GRAM_ARGS);                 \
       break;                                                                                   \
     }                                                                                          \
     break;
+  cudaError_t launch_err = cudaSuccess;
   switch (dim) {
     AB_GRAM_CASE(1)
     AB_GRAM_CASE(2)
@@ -738,8 +276,10 @@ static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *
     set_error("feature dimension %d has no device form (1..%d supported)", dim, AB_MAX_DIM);
     return AB_ERR_UNSUPPORTED;
   }
+#undef AB_GRAM_ARGS
 #undef AB_GRAM_CASE
-  AB_LAUNCHED(h);
+  AB_CUDA(launch_err);
+  h->launches++;
   return AB_OK;
 }
 

@@ -1,0 +1,687 @@
+// The Gram tile kernel (version 2) and its two evaluator families.
+//
+// One CTA (256 threads, 2 CTAs / SM) computes one 64 x 64 tile of K_ij = k(x_i, y_j); a thread owns
+// 2 rows x 4 columns per pass (8 pairs in flight, 2 passes).  For the symmetric build only tiles on
+// or below the diagonal are evaluated and the transposed tile is written from a shared-memory
+// staging buffer, so that both orientations leave the SM as full 256/512-byte row segments.
+//
+// The round-1 profile (profiles/r01_ncu_gram_gemm_summary.md) showed the first version issue-bound:
+// 122 warp instructions per pair of which only 40 are FP64 arithmetic.  This version removes the
+// rest as far as the algorithm allows:
+//   * interior tiles take a path without any bounds checks and with pointer-increment addressing;
+//   * the exp / sqrt argument range checks are one signed min/max per 8 values (VIMNMX3) instead
+//     of three integer instructions per value; out-of-range batches take a patch-up branch;
+//   * the 2^n scaling of exp is LOP3 + IMAD, the table index LOP3 + LEA;
+//   * the triangular tile decode is 32-bit (fp32 sqrt + integer fix-up);
+//   * EvalFixed<K0, K1, K2> evaluates a sum of up to three leaves whose kinds are template
+//     parameters (the reference composes covariance functions at compile time too,
+//     covariance_functions/covariance_function.hpp:222-420): no op loop, no decode branches.
+//     EvalProgram<MODE> keeps the generic run-time program (sum of products / postfix stack).
+#pragma once
+
+#include "exp_table.cuh"
+#include "gram.cuh"
+
+namespace ab {
+
+constexpr int TILE = 64;
+constexpr int LDT = TILE + 1;
+constexpr int GRAM_THREADS = 256;
+// A thread owns 2 rows x COLS columns per pass (2 * COLS pairs in flight); 8 / COLS passes cover the
+// 64 columns of the tile.
+
+// ------------------------------------------------------------------------------------------------
+// lean fp64 exp / sqrt
+// ------------------------------------------------------------------------------------------------
+
+// exp(x) for -708 <= x <= -0 (the argument of every radial kernel): x = (128 n + j) ln2/128 + r,
+// exp(x) = 2^n T[j] (1 + r + ... + r^5/120), |r| <= ln2/256; 10 FP64-pipe instructions, <= 1 ulp.
+// hi_max accumulates the signed maximum of the arguments' high words: the batch is in range iff
+// hi_max <= (int)0xC0862000 (-708.0); +0, positive values, x < -708, +-inf and NaN all compare
+// greater and are patched by the caller.
+__device__ __forceinline__ double exp_core(double x, const double *__restrict__ tab, int &hi_max) {
+  const double t = fma(x, 184.6649652337873, 6755399441055744.0); // x * 128/ln2, round to nearest
+  const int m = __double2loint(t);
+  const double mf = t - 6755399441055744.0;
+  double r = fma(mf, -0x1.62e42fef00000p-8, x); // ln2/128 high part (32 significant bits)
+  r = fma(mf, -0x1.473de6af278edp-41, r);       // ln2/128 low part
+  double p = fma(r, 0.008333333333333333, 0.041666666666666664);
+  p = fma(p, r, 0.16666666666666666);
+  p = fma(p, r, 0.5);
+  const double r2 = r * r;
+  const double q = fma(p, r2, r); // expm1(r)
+  const double tj = tab[m & 127];
+  const double res = fma(tj, q, tj);
+  hi_max = max(hi_max, __double2hiint(x));
+  // + n * 2^20 on the high word, n = m >> 7 (arithmetic): (m & ~127) * 2^13
+  return __hiloint2double(__double2hiint(res) + (m & ~127) * 8192, __double2loint(res));
+}
+
+// Same with the 2048-entry table: |r| <= ln2/4096, degree-3 polynomial, 8 FP64-pipe instructions,
+// <= 1.3 ulp (tools/make_exp_table.py generates both tables).
+__device__ __forceinline__ double exp_core_big(double x, const double *__restrict__ tab,
+                                               int &hi_max) {
+  const double t = fma(x, 2954.639443740597, 6755399441055744.0); // x * 2048/ln2
+  const int m = __double2loint(t);
+  const double mf = t - 6755399441055744.0;
+  double r = fma(mf, -0x1.62e42fef00000p-12, x);
+  r = fma(mf, -0x1.473de6af278edp-45, r);
+  const double p = fma(r, 0.16666666666666666, 0.5);
+  const double r2 = r * r;
+  const double q = fma(p, r2, r); // expm1(r)
+  const double tj = tab[m & 2047];
+  const double res = fma(tj, q, tj);
+  hi_max = max(hi_max, __double2hiint(x));
+  return __hiloint2double(__double2hiint(res) + (m & ~2047) * 512, __double2loint(res));
+}
+
+constexpr int EXP_HI_LIMIT = static_cast<int>(0xC0862000u);
+
+__device__ __forceinline__ double exp_patch(double x, double fast) {
+  // x == +0 or in range: the fast value is right; x < -708: the reference's exp() underflows to a
+  // subnormal < 3e-308 or 0, flushed to 0 here; NaN propagates.  x > 0 cannot occur: every radial
+  // argument is (negative coefficient) * (distance >= 0).
+  return (x < -708.0) ? 0. : ((x != x) ? x : fast);
+}
+
+// sqrt(a) for positive normal a: MUFU.RSQ64H seed (~2^-22) + one Goldschmidt step on g ~ sqrt(a)
+// + residual correction with the un-refined h ~ 1/(2 sqrt(a)) (its 2^-22 error only scales a
+// 2^-44 correction): 6 FP64-pipe instructions, 0.51 ulp measured.  Valid iff 0x00100000 <= hi(a) <= 0x7fefffff (signed), which
+// the caller checks once per batch through hi_min / hi_max.
+__device__ __forceinline__ double sqrt_core(double a, int &hi_min, int &hi_max) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y;
+  double h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  const double e = fma(-g, g, a);
+  const int hi = __double2hiint(a);
+  hi_min = min(hi_min, hi);
+  hi_max = max(hi_max, hi);
+  return fma(e, h, g);
+}
+
+__device__ __forceinline__ double sqrt_patch(double a, double fast) {
+  if (a >= 2.2250738585072014e-308 && a < INFINITY) {
+    return fast;
+  }
+  if (a > 0. && a < INFINITY) { // subnormal: rescale by 2^108
+    int lo = 0x7fffffff, hi = 0;
+    return sqrt_core(a * 3.2451855365842673e32, lo, hi) * 5.551115123125783e-17;
+  }
+  return a; // 0, inf, NaN map to themselves (negative cannot occur: a is a sum of squares)
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluators
+// ------------------------------------------------------------------------------------------------
+
+constexpr int MODE_SUM = 0, MODE_SUM_NOISE = 1, MODE_SOP = 2, MODE_STACK = 3;
+
+// exp of NP arguments with one range check for the batch
+template <int NP, bool BIG = false>
+__device__ __forceinline__ void exp_batch(const double (&v)[NP], const double *__restrict__ tab,
+                                          double (&e)[NP]) {
+  int hi_max = EXP_HI_LIMIT;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    e[i] = BIG ? exp_core_big(v[i], tab, hi_max) : exp_core(v[i], tab, hi_max);
+  }
+  if (hi_max > EXP_HI_LIMIT) { // rare
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      e[i] = exp_patch(v[i], e[i]);
+    }
+  }
+}
+
+// Run-time program, sum-of-products form (gram.cuh): the op loop is uniform across the CTA and its
+// decode cost is amortised over the NP pairs a thread owns.
+template <int NP, int MODE>
+__device__ __forceinline__ void eval_sop(const DevProg &P, const double (&d2)[NP],
+                                         const double (&dist)[NP], unsigned eqmask,
+                                         const double *__restrict__ tab, double (&out)[NP]) {
+  double prod[MODE >= MODE_SOP ? NP : 1];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    out[i] = 0.;
+  }
+  for (int k = 0; k < P.nops; ++k) {
+    const int kind = P.ops[k].kind;
+    const int flags = P.ops[k].flags;
+    const double amp = P.ops[k].amp;
+    double v[NP];
+    if (kind == DK_RADIAL) {
+      if (flags & DF_USES_DIST) {
+        const double a1 = P.ops[k].a1;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          v[i] = a1 * dist[i];
+        }
+      } else {
+        const double a2 = P.ops[k].a2;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          v[i] = a2 * d2[i];
+        }
+      }
+      double e[NP];
+      exp_batch<NP>(v, tab, e);
+      if (flags & DF_POLY_D1) {
+        const double b1 = P.ops[k].b1;
+        if (flags & DF_POLY_D2) {
+          const double b2 = P.ops[k].b2;
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            v[i] = e[i] * fma(b2, d2[i], fma(b1, dist[i], 1.));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            v[i] = e[i] * fma(b1, dist[i], 1.);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          v[i] = e[i];
+        }
+      }
+    } else if (MODE >= MODE_SUM_NOISE && kind == DK_NOISE) {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i] = ((eqmask >> i) & 1u) ? 1. : 0.;
+      }
+    } else {
+      const double c = kind == DK_CONST ? 1. : 0.;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i] = c;
+      }
+    }
+    if (MODE < MODE_SOP ||
+        (flags & (DF_TERM_START | DF_TERM_END)) == (DF_TERM_START | DF_TERM_END)) {
+      // single-leaf term: out += amp * v  (out starts at +0, so the first term is exact)
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        out[i] = fma(amp, v[i], out[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i] *= amp;
+      }
+      if (!(flags & DF_TERM_START)) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const double pr = prod[MODE >= MODE_SOP ? i : 0];
+          v[i] = (pr != 0.) ? pr * v[i] : pr; // covariance_function.hpp:362-366
+        }
+      }
+      if (flags & DF_TERM_END) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          out[i] += v[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          prod[MODE >= MODE_SOP ? i : 0] = v[i];
+        }
+      }
+    }
+  }
+}
+
+__device__ __noinline__ double eval_stack(const DevProg &P, double d2, double dist, bool equal);
+
+template <int MODE> struct EvalProgram {
+  static constexpr bool NEED_EQ = MODE != MODE_SUM;
+  static constexpr int TABLE = 128;
+  __device__ static __forceinline__ const double *table() { return EXP_TABLE; }
+  __device__ static __forceinline__ bool need_dist(const DevProg &P) { return P.need_dist != 0; }
+  template <int NP>
+  __device__ static __forceinline__ void run(const DevProg &P, const double (&d2)[NP],
+                                             const double (&dist)[NP], unsigned eqmask,
+                                             const double *__restrict__ tab, double (&out)[NP]) {
+    if (MODE != MODE_STACK) {
+      eval_sop<NP, MODE>(P, d2, dist, eqmask, tab, out);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        out[i] = eval_stack(P, d2[i], dist[i], (eqmask >> i) & 1u);
+      }
+    }
+  }
+};
+
+// Compile-time leaf kinds of EvalFixed.
+enum LeafSig : int { LS_NONE = 0, LS_SE = 1, LS_EXP = 2, LS_M32 = 3, LS_M52 = 4, LS_CONST = 5, LS_NOISE = 6 };
+
+template <int KIND, int NP, bool BIG>
+__device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP],
+                                           const double (&dist)[NP], unsigned eqmask,
+                                           const double *__restrict__ tab, double (&out)[NP]) {
+  if constexpr (KIND == LS_NONE) {
+    return;
+  } else if constexpr (KIND == LS_CONST) {
+    const double amp = o.amp;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      out[i] = fma(amp, 1., out[i]);
+    }
+  } else if constexpr (KIND == LS_NOISE) {
+    const double amp = o.amp;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      out[i] = fma(amp, ((eqmask >> i) & 1u) ? 1. : 0., out[i]);
+    }
+  } else {
+    double v[NP], e[NP];
+    if constexpr (KIND == LS_SE) {
+      const double a2 = o.a2;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i] = a2 * d2[i];
+      }
+    } else {
+      const double a1 = o.a1;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i] = a1 * dist[i];
+      }
+    }
+    exp_batch<NP, BIG>(v, tab, e);
+    if constexpr (KIND == LS_M32) {
+      const double b1 = o.b1;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        e[i] = e[i] * fma(b1, dist[i], 1.);
+      }
+    } else if constexpr (KIND == LS_M52) {
+      const double b1 = o.b1, b2 = o.b2;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        e[i] = e[i] * fma(b2, d2[i], fma(b1, dist[i], 1.));
+      }
+    }
+    const double amp = o.amp;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      out[i] = fma(amp, e[i], out[i]);
+    }
+  }
+}
+
+// Sum of up to three single leaves with compile-time kinds; arithmetic identical to
+// eval_sop<MODE_SUM / MODE_SUM_NOISE> on the same program (same operations in the same order).
+template <int K0, int K1, int K2, bool BIG = true> struct EvalFixed {
+  static constexpr bool NEED_EQ = K0 == LS_NOISE || K1 == LS_NOISE || K2 == LS_NOISE;
+  static constexpr int TABLE = BIG ? 2048 : 128;
+  __device__ static __forceinline__ const double *table() { return BIG ? EXP_TABLE_BIG : EXP_TABLE; }
+  static constexpr bool NEED_DIST = (K0 >= LS_EXP && K0 <= LS_M52) || (K1 >= LS_EXP && K1 <= LS_M52) ||
+                                    (K2 >= LS_EXP && K2 <= LS_M52);
+  __device__ static __forceinline__ bool need_dist(const DevProg &) { return NEED_DIST; }
+  template <int NP>
+  __device__ static __forceinline__ void run(const DevProg &P, const double (&d2)[NP],
+                                             const double (&dist)[NP], unsigned eqmask,
+                                             const double *__restrict__ tab, double (&out)[NP]) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      out[i] = 0.;
+    }
+    fixed_term<K0, NP, BIG>(P.ops[0], d2, dist, eqmask, tab, out);
+    fixed_term<K1, NP, BIG>(P.ops[1], d2, dist, eqmask, tab, out);
+    fixed_term<K2, NP, BIG>(P.ops[2], d2, dist, eqmask, tab, out);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the tile kernel
+// ------------------------------------------------------------------------------------------------
+
+// Work item t of the launch -> tile (I, J); returns false for items that carry no tile.
+//   SYM: the lower triangle is walked in SB x SB super-blocks of tiles (row by row over the
+//        super-blocks, t = (B_I (B_I + 1) / 2 + B_J) * SB^2 + local), rows fastest inside a
+//        super-block.  The ~300 tiles in flight at any time then cover a compact 2-D patch of K, so
+//        that both the direct stores (contiguous along rows) and the mirrored ones stay within a
+//        few hundred 2 MB pages instead of sweeping every column of K for each row of tiles
+//        (measured store-bound rates before: 5.3 TB/s at N = 16 384 falling to 4.5 TB/s at 49 152).
+//        Items above the diagonal or beyond the last tile row are skipped.  32-bit arithmetic is
+//        exact: the launcher caps the item count at 2^31.
+//   otherwise column-major over the tiles_i x tiles_j grid (rows fastest: contiguous stores).
+constexpr unsigned SB = 16;
+
+template <bool SYM>
+__device__ __forceinline__ bool decode_tile(unsigned t, unsigned tiles_i, unsigned &I, unsigned &J) {
+  if (SYM) {
+    const unsigned sb = t / (SB * SB);
+    const unsigned local = t % (SB * SB);
+    unsigned i = static_cast<unsigned>((sqrtf(8.f * static_cast<float>(sb) + 1.f) - 1.f) * 0.5f);
+    while (i * (i + 1u) / 2u > sb) {
+      --i;
+    }
+    while ((i + 1u) * (i + 2u) / 2u <= sb) {
+      ++i;
+    }
+    I = i * SB + local % SB;
+    J = (sb - i * (i + 1u) / 2u) * SB + local / SB;
+    return I < tiles_i && J <= I;
+  }
+  I = t % tiles_i;
+  J = t / tiles_i;
+  return true;
+}
+
+// First work item >= t (stepping by `step`) that carries a tile, decoded into (I, J).
+template <bool SYM>
+__device__ __forceinline__ unsigned next_tile(unsigned t, unsigned step, unsigned nitems,
+                                              unsigned tiles_i, unsigned &I, unsigned &J) {
+  while (t < nitems && !decode_tile<SYM>(t, tiles_i, I, J)) {
+    t += step;
+  }
+  return t;
+}
+
+// Number of work items of a launch (see decode_tile).
+inline int64_t gram_items(bool sym, int64_t tiles_i, int64_t tiles_j) {
+  if (!sym) {
+    return tiles_i * tiles_j;
+  }
+  const int64_t nsb = (tiles_i + SB - 1) / SB;
+  return nsb * (nsb + 1) / 2 * SB * SB;
+}
+
+constexpr int FEAT_SLOTS = 2; // TILE * AB_MAX_DIM / GRAM_THREADS feature elements per thread
+
+// This thread's share of the x / y features of tile (I, J), straight from global memory.
+template <int DIM>
+__device__ __forceinline__ void fetch_features(const double *__restrict__ fx, int64_t ldfx,
+                                               int64_t n, const double *__restrict__ fy,
+                                               int64_t ldfy, int64_t m, unsigned I, unsigned J,
+                                               int tid, double (&px)[FEAT_SLOTS],
+                                               double (&py)[FEAT_SLOTS]) {
+  const int64_t i0 = static_cast<int64_t>(I) * TILE;
+  const int64_t j0 = static_cast<int64_t>(J) * TILE;
+#pragma unroll
+  for (int e = 0; e < FEAT_SLOTS; ++e) {
+    const int idx = tid + e * GRAM_THREADS;
+    px[e] = 0.;
+    py[e] = 0.;
+    if (idx < TILE * DIM) {
+      const int p = idx / DIM;
+      const int d = idx - p * DIM;
+      if (i0 + p < n) {
+        px[e] = fx[(i0 + p) * ldfx + d];
+      }
+      if (j0 + p < m) {
+        py[e] = fy[(j0 + p) * ldfy + d];
+      }
+    }
+  }
+}
+
+// One slice (1 / PARTS) of the transposed copy of a finished tile: element (row = j0 + c,
+// col = i0 + r) = stage[c][r]; each warp-store covers 32 consecutive rows (256 contiguous bytes).
+template <int PARTS>
+__device__ __forceinline__ void mirror_slice(const double *__restrict__ stage,
+                                             double *__restrict__ out, int64_t ld, int64_t n,
+                                             unsigned I, unsigned J, bool interior, int part,
+                                             int lane, int warp) {
+  constexpr int KS = 8 / PARTS;
+  const int64_t i0 = static_cast<int64_t>(I) * TILE;
+  const int64_t j0 = static_cast<int64_t>(J) * TILE;
+  const int rbase = warp * 8 + part * KS;
+  if (interior) {
+    double *dst = out + (j0 + lane) + (i0 + rbase) * ld;
+    const double *src = stage + lane * LDT + rbase;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      dst[0] = src[k];
+      dst[32] = src[32 * LDT + k];
+      dst += ld;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int r = rbase + k;
+      const int64_t gcol = i0 + r;
+      if (gcol < n) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c = lane + 32 * half;
+          const int64_t grow = j0 + c;
+          if (grow < n) {
+            out[grow + gcol * ld] = stage[c * LDT + r];
+          }
+        }
+      }
+    }
+  }
+}
+
+// Persistent CTAs: each CTA walks the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+//   * the features of the next tile are fetched into registers while the current one is evaluated
+//     (global-load latency, table load and the store drain at exit are paid once per CTA);
+//   * the transposed copy of tile k is written while tile k+1 is being evaluated: the staging
+//     buffer is double-buffered and one slice of the pending mirror is issued after every pass, so
+//     the LDS/STG traffic of the mirror hides behind FP64 work instead of forming a phase of its own
+//     (measured: the separate mirror phase cost 0.53 ms of 2.28 ms at N = 32 768).
+template <int DIM, bool SYM, class EV, int COLS = 4, int MINB = 2>
+__global__ void __launch_bounds__(GRAM_THREADS, MINB)
+gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, int64_t ldfx,
+            int64_t n, const double *__restrict__ fy, int64_t ldfy, int64_t m,
+            double *__restrict__ out, int64_t ld, int tiles_i, unsigned ntiles, uint32_t flags) {
+  constexpr int NPAIR = 2 * COLS;
+  constexpr int PASSES = 8 / COLS;
+  constexpr int STAGE = TILE * LDT;
+  // dynamic shared memory (gram_smem_bytes): exp table | x features | y features | 2 x mirror staging
+  extern __shared__ __align__(16) double gram_smem[];
+  double *tab = gram_smem;
+  double *xs = tab + EV::TABLE;
+  double *ys = xs + TILE * DIM;
+  double *stage0 = ys + TILE * DIM;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int r0 = 2 * lane;
+  for (int idx = tid; idx < EV::TABLE; idx += GRAM_THREADS) {
+    tab[idx] = EV::table()[idx];
+  }
+  const bool need_dist = DIM != 1 && EV::need_dist(P);
+
+  unsigned t = blockIdx.x;
+  unsigned I = 0, J = 0;
+  double px[FEAT_SLOTS], py[FEAT_SLOTS];
+  t = next_tile<SYM>(t, gridDim.x, ntiles, static_cast<unsigned>(tiles_i), I, J);
+  if (t < ntiles) {
+    fetch_features<DIM>(fx, ldfx, n, fy, ldfy, m, I, J, tid, px, py);
+  }
+  // pending mirror of the previous tile: bit 0 = pending, bit 1 = interior, bit 2 = staging buffer
+  unsigned pend = 0, pI = 0, pJ = 0;
+  unsigned buf = 0;
+
+  while (t < ntiles) {
+    const unsigned cI = I, cJ = J;
+    const int64_t i0 = static_cast<int64_t>(cI) * TILE;
+    const int64_t j0 = static_cast<int64_t>(cJ) * TILE;
+    const bool mirror = SYM && cI != cJ && !(flags & AB_GRAM_LOWER_ONLY);
+    // interior tile of a 16-byte aligned output: no bounds checks anywhere below
+    const bool interior = (i0 + TILE <= n) && (j0 + TILE <= m) && !(flags & GRAM_UNALIGNED);
+    double *stage = stage0 + buf * STAGE;
+
+    // every reader of xs / ys of the previous tile is done, every slice of the mirror before the
+    // pending one has been read, and the pending tile's staging buffer is completely written
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < FEAT_SLOTS; ++e) {
+      const int idx = tid + e * GRAM_THREADS;
+      if (idx < TILE * DIM) {
+        xs[idx] = px[e];
+        ys[idx] = py[e];
+      }
+    }
+    __syncthreads();
+
+    // prefetch the next tile's features; they are consumed at the top of the next iteration
+    t = next_tile<SYM>(t + gridDim.x, gridDim.x, ntiles, static_cast<unsigned>(tiles_i), I, J);
+    if (t < ntiles) {
+      fetch_features<DIM>(fx, ldfx, n, fy, ldfy, m, I, J, tid, px, py);
+    }
+
+    double xi[2][DIM];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        xi[a][d] = xs[(r0 + a) * DIM + d];
+      }
+    }
+    const int64_t gi = i0 + r0;
+
+#pragma unroll 1
+    for (int pass = 0; pass < PASSES; ++pass) {
+      const int cbase = pass * (8 * COLS) + warp * COLS;
+      double d2[NPAIR], dist[NPAIR], vals[NPAIR];
+      unsigned eqmask = 0;
+#pragma unroll
+      for (int k = 0; k < COLS; ++k) {
+        const int c = cbase + k;
+        double yj[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+          yj[d] = ys[c * DIM + d];
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          double s = 0.;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) {
+            const double diff = xi[a][d] - yj[d];
+            s = fma(diff, diff, s);
+          }
+          d2[2 * k + a] = s;
+          dist[2 * k + a] = DIM == 1 ? fabs(xi[a][0] - yj[0]) : 0.;
+          if (EV::NEED_EQ) {
+            bool eq = true;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+              eq = eq && (xi[a][d] == yj[d]);
+            }
+            eqmask |= (eq ? 1u : 0u) << (2 * k + a);
+          }
+        }
+      }
+      if (need_dist) {
+        int hi_min = 0x00100000, hi_max = 0x7fefffff;
+#pragma unroll
+        for (int i = 0; i < NPAIR; ++i) {
+          dist[i] = sqrt_core(d2[i], hi_min, hi_max);
+        }
+        if (hi_min < 0x00100000 || hi_max > 0x7fefffff) {
+          // rare: a zero / subnormal / non-finite squared distance (e.g. the diagonal)
+#pragma unroll
+          for (int i = 0; i < NPAIR; ++i) {
+            dist[i] = sqrt_patch(d2[i], dist[i]);
+          }
+        }
+      }
+
+      EV::template run<NPAIR>(P, d2, dist, eqmask, tab, vals);
+
+      // direct tile: rows i0 + r0 (+1), columns j0 + c; 16-byte stores, 512 contiguous bytes/warp
+      if (interior) {
+        double *dst = out + gi + (j0 + cbase) * ld;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) {
+          *reinterpret_cast<double2 *>(dst) = make_double2(vals[2 * k], vals[2 * k + 1]);
+          dst += ld;
+        }
+      } else {
+        const bool unaligned = flags & GRAM_UNALIGNED;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) {
+          const int64_t gj = j0 + cbase + k;
+          if (gj < m) {
+            double *dst = out + gi + gj * ld;
+            if (gi + 1 < n && !unaligned) {
+              *reinterpret_cast<double2 *>(dst) = make_double2(vals[2 * k], vals[2 * k + 1]);
+            } else if (gi < n) {
+              dst[0] = vals[2 * k];
+              if (gi + 1 < n) {
+                dst[1] = vals[2 * k + 1];
+              }
+            }
+          }
+        }
+      }
+      if (mirror) {
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) {
+          const int c = cbase + k;
+          stage[c * LDT + r0] = vals[2 * k];
+          stage[c * LDT + r0 + 1] = vals[2 * k + 1];
+        }
+      }
+      if (SYM && (pend & 1u)) {
+        mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
+                             pass, lane, warp);
+      }
+    }
+
+    if (SYM) {
+      pend = mirror ? (1u | (interior ? 2u : 0u) | (buf << 2)) : 0u;
+      pI = cI;
+      pJ = cJ;
+      if (mirror) {
+        buf ^= 1u;
+      }
+    }
+  }
+
+  if (SYM && (pend & 1u)) { // the last tile's mirror has no next tile to hide behind
+    __syncthreads();
+#pragma unroll 1
+    for (int part = 0; part < PASSES; ++part) {
+      mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u, part,
+                           lane, warp);
+    }
+  }
+}
+
+template <int DIM, bool SYM, class EV> constexpr size_t gram_smem_bytes() {
+  return sizeof(double) * (EV::TABLE + 2 * TILE * DIM + (SYM ? 2 * TILE * LDT : 0));
+}
+
+// Launches the persistent kernel: MINB CTAs per SM (or one per tile when there are fewer tiles).
+template <int DIM, bool SYM, class EV, int COLS = 4, int MINB = 2>
+inline cudaError_t gram_launch(ab_handle_s *h, const DevProg &P, const double *fx, int64_t ldfx,
+                               int64_t n, const double *fy, int64_t ldfy, int64_t m, double *out,
+                               int64_t ld, int tiles_i, unsigned ntiles, uint32_t flags) {
+  constexpr size_t smem = gram_smem_bytes<DIM, SYM, EV>();
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gram_kernel<DIM, SYM, EV, COLS, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      return e;
+    }
+    configured = true;
+  }
+  const int64_t resident = static_cast<int64_t>(MINB) * h->sm_count;
+  const unsigned grid = static_cast<unsigned>(ntiles < resident ? ntiles : resident);
+  gram_kernel<DIM, SYM, EV, COLS, MINB><<<grid, GRAM_THREADS, smem, h->stream>>>(
+      P, fx, ldfx, n, fy, ldfy, m, out, ld, tiles_i, ntiles, flags);
+  return cudaGetLastError();
+}
+
+// Launch of the compile-time-specialised kernels (gram_fixed.cu).  Returns true when the program
+// has a specialisation (and the launch was issued), false when the generic kernel must be used.
+bool launch_gram_fixed(ab_handle_s *h, const DevProg &P, int dim, bool sym, const double *fx,
+                       int64_t ldfx, int64_t n, const double *fy, int64_t ldfy, int64_t m,
+                       double *out, int64_t ld, int tiles_i, unsigned tiles, uint32_t flags);
+
+} // namespace ab

@@ -1,0 +1,40 @@
+"""Times the Gram kernel in isolation (development aid): python tools/gram_bench.py [n] [cov_id] [dim]."""
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from albatross_b200 import capi  # noqa: E402
+from oracle.oracle import menu_program  # noqa: E402
+
+PARAMS = {4: [1.3], 0: [2.0, 1.5], 3: [3.0, 0.7], 6: [1.0, 1.0, 0.1], 7: [2.0, 1.5, 3.0, 0.7],
+          8: [2.0, 1.5, 3.0, 0.7, 0.1], 9: [2.0, 1.5, 3.0, 0.7, 1.1, 0.9, 1.2, 0.3]}
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+    cid = int(sys.argv[2]) if len(sys.argv) > 2 else 7
+    dim = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    reps = int(sys.argv[4]) if len(sys.argv) > 4 else 6
+    flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    cross = len(sys.argv) > 6 and sys.argv[6] == "cross"
+    h = capi.Handle(0)
+    ops, pp = menu_program(cid, PARAMS[cid])
+    x = np.random.default_rng(0).uniform(0, 10, size=(n, dim))
+    fd = h.upload_features(x)
+    flush = h.alloc(8192, 8192)  # 512 MiB > L2
+    best = 1e30
+    for rep in range(reps):
+        flush.add_diag(np.full(8192, float(rep)))
+        K = h.gram_cross_d(ops, pp, fd, fd) if cross else h.gram_sym_d(ops, pp, fd, flags=flags)
+        ms = h.timings()["gram_ms"]
+        K.free()
+        if rep > 0:
+            best = min(best, ms)
+        print(f"rep {rep}: {ms:.3f} ms", flush=True)
+    gb = (8.0 * n * n + 8.0 * n * dim) * 1e-9
+    print(f"gram n={n} cov={cid} dim={dim} flags={flags} cross={cross}: best {best:.3f} ms  {gb / best * 1e3:.1f} GB/s")
+
+
+if __name__ == "__main__":
+    main()
