@@ -57,7 +57,7 @@ SYMBOLS = [
     "ab_factor_sqrt_solve", "ab_factor_logdet", "ab_factor_nll", "ab_factor_inverse_diagonal",
     "ab_factor_inverse_blocks", "ab_factor_export_packed", "ab_gp_fit", "ab_gp_nll",
     "ab_gp_fit_nll", "ab_gp_predict", "ab_gp_cv", "ab_gp_fit_d", "ab_gp_nll_d",
-    "ab_group_indexers", "ab_gemm", "ab_gp_cv_shard",
+    "ab_group_indexers", "ab_gemm", "ab_gp_cv_shard", "ab_gp_cv_scores", "ab_gp_predict2",
     "ab_sparse_fit", "ab_sparse_free", "ab_sparse_info", "ab_sparse_log_likelihood",
     "ab_sparse_predict", "ab_sparse_export_R",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",

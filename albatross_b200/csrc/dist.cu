@@ -595,7 +595,7 @@ int ab_dist_gp_cv(ab_handle h, ab_factor factor, const double *y, const double *
   const int64_t n = factor->n;
   double local_score = 0.;
   AB_TRY(gp_cv_impl(h, factor, y, information, indices, offsets, ngroups, what, h->rank, h->world,
-                    mean, var, nullptr, score != nullptr ? &local_score : nullptr));
+                    mean, var, nullptr, score != nullptr ? &local_score : nullptr, nullptr));
   if (h->world > 1 && n > 0) {
     // assemble: every observation was written by exactly one rank, the others hold zero
     Scope sc(h);

@@ -584,9 +584,10 @@ int ab_gp_fit_nll(ab_handle h, const ab_op *prog, int nops, const double *feats,
   return ab_factor_nll(h, *factor, y, nll);
 }
 
-int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const double *train_feats,
-                  int64_t n, int dim, const double *information, const double *test_feats,
-                  int64_t p, int what, double *mean, double *var, double *cov) {
+static int gp_predict_impl(ab_handle h, ab_factor f, const ab_op *prog, int nops,
+                           const ab_op *prior_prog, int prior_nops, const double *train_feats,
+                           int64_t n, int dim, const double *information, const double *test_feats,
+                           int64_t p, int what, double *mean, double *var, double *cov) {
   AB_REQUIRE(h != nullptr && train_feats != nullptr && information != nullptr && p >= 0 &&
                  (p == 0 || (test_feats != nullptr && mean != nullptr)),
              "null");
@@ -599,8 +600,9 @@ int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const d
   if (p == 0) {
     return AB_OK;
   }
-  DevProg P;
+  DevProg P, PP;
   AB_TRY(compile_program(prog, nops, &P));
+  AB_TRY(compile_program(prior_prog, prior_nops, &PP));
   Scope sc(h);
   timings_reset(h);
   ab_matrix_s *FX = nullptr, *FT = nullptr, *info = nullptr, *cross = nullptr, *m = nullptr;
@@ -625,7 +627,7 @@ int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const d
     void *d_prior = nullptr, *d_expl = nullptr;
     AB_TRY(sc.alloc(static_cast<size_t>(p) * sizeof(double), &d_prior));
     AB_TRY(sc.alloc(static_cast<size_t>(p) * sizeof(double), &d_expl));
-    AB_TRY(gram_diag_device(h, P, FT, static_cast<double *>(d_prior)));
+    AB_TRY(gram_diag_device(h, PP, FT, static_cast<double *>(d_prior)));
     AB_TRY(trsm_left_lower(h, view(f->m), f->dinv, n, view(cross), p));
     AB_TRY(column_dots(h, view(cross), view(cross), n, p, static_cast<double *>(d_expl)));
     phase_end(h, PH_PREDICT);
@@ -638,7 +640,7 @@ int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const d
   } else if (what == AB_PREDICT_JOINT) {
     // cov = K(test,test) - (L^-1 cross)^T (L^-1 cross)  (gp.hpp:103-113)
     ab_matrix_s *prior = nullptr;
-    AB_TRY(gram_sym_device(h, P, FT, AB_GRAM_FULL, &prior));
+    AB_TRY(gram_sym_device(h, PP, FT, AB_GRAM_FULL, &prior));
     sc.own(prior);
     AB_TRY(trsm_left_lower(h, view(f->m), f->dinv, n, view(cross), p));
     AB_TRY(gemm(h, GEMM_TRANS_A, p, p, n, -1., view(cross), view(cross), 1., view(prior)));
@@ -649,6 +651,21 @@ int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const d
   }
   cudaEventRecord(h->ev_total_end, h->stream);
   return download(h, m, 0, 0, p, 1, mean);
+}
+
+int ab_gp_predict(ab_handle h, ab_factor f, const ab_op *prog, int nops, const double *train_feats,
+                  int64_t n, int dim, const double *information, const double *test_feats,
+                  int64_t p, int what, double *mean, double *var, double *cov) {
+  return gp_predict_impl(h, f, prog, nops, prog, nops, train_feats, n, dim, information,
+                         test_feats, p, what, mean, var, cov);
+}
+
+int ab_gp_predict2(ab_handle h, ab_factor f, const ab_op *cross_prog, int cross_nops,
+                   const ab_op *prior_prog, int prior_nops, const double *train_feats, int64_t n,
+                   int dim, const double *information, const double *test_feats, int64_t p,
+                   int what, double *mean, double *var, double *cov) {
+  return gp_predict_impl(h, f, cross_prog, cross_nops, prior_prog, prior_nops, train_feats, n, dim,
+                         information, test_feats, p, what, mean, var, cov);
 }
 
 } // extern "C"
@@ -675,11 +692,16 @@ static int inverse_diagonal_chunk(ab_handle_s *h, const ab_factor_s *f, int64_t 
 // through one explicit inverse factor (N^3/3); stride > 1: per-shard triangular solves.
 int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *information,
                const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
-               int phase, int stride, double *mean, double *var, double *joint, double *score) {
+               int phase, int stride, double *mean, double *var, double *joint, double *score,
+               double *group_scores) {
   const int64_t n = f->n;
   if (score != nullptr) {
     *score = 0.;
   }
+  if (group_scores != nullptr) {
+    std::fill(group_scores, group_scores + ngroups, 0.);
+  }
+  const bool want_score = score != nullptr || group_scores != nullptr;
   if (ngroups == 0 || n == 0) {
     return AB_OK;
   }
@@ -758,13 +780,18 @@ int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *in
         }
       }
     }
-    if (score != nullptr) {
+    if (want_score) {
       std::vector<double> t(n);
       AB_TRY(download_bytes(h, d_terms, nbytes, t.data()));
       for (int64_t g = 0; g < n; ++g) {
         total_score += t[indices[offsets[g]]];
+        if (group_scores != nullptr) {
+          group_scores[g] = t[indices[offsets[g]]];
+        }
       }
-      *score = total_score;
+      if (score != nullptr) {
+        *score = total_score;
+      }
     }
     cudaEventRecord(h->ev_total_end, h->stream);
     return AB_OK;
@@ -838,7 +865,7 @@ int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *in
         static_cast<double *>(d_y), x->d, diag, gi, k, static_cast<double *>(d_mean),
         diag != nullptr ? static_cast<double *>(d_var) : nullptr);
     AB_LAUNCHED(h);
-    if (score != nullptr) {
+    if (want_score) {
       // NLL(dev = x, cov = A^-1) = 0.5 (-logdet(A) + x^T A x + k log 2pi), x^T A x = x . v_g
       AB_TRY(logdet_chol(h, view(A), k, static_cast<double *>(d_gscal) + 2 * g));
       AB_TRY(dot(h, x->d, x->d + x->ld, k, static_cast<double *>(d_gscal) + 2 * g + 1));
@@ -858,7 +885,7 @@ int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *in
     set_error("a held-out block of the inverse covariance is not positive definite");
     return AB_ERR_NOT_PD;
   }
-  if (score != nullptr) {
+  if (want_score) {
     std::vector<double> gs(static_cast<size_t>(ngroups) * 2);
     AB_TRY(download_bytes(h, d_gscal, gs.size() * sizeof(double), gs.data()));
     for (int64_t g = 0; g < ngroups; ++g) {
@@ -866,9 +893,16 @@ int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *in
       if (k == 0 || g % stride != phase) {
         continue;
       }
-      total_score += 0.5 * (-gs[2 * g] + gs[2 * g + 1] + static_cast<double>(k) * std::log(2 * M_PI));
+      const double sg =
+          0.5 * (-gs[2 * g] + gs[2 * g + 1] + static_cast<double>(k) * std::log(2 * M_PI));
+      total_score += sg;
+      if (group_scores != nullptr) {
+        group_scores[g] = sg;
+      }
     }
-    *score = total_score;
+    if (score != nullptr) {
+      *score = total_score;
+    }
   }
   cudaEventRecord(h->ev_total_end, h->stream);
   return AB_OK;
@@ -891,7 +925,24 @@ int ab_gp_cv(ab_handle h, ab_factor f, const double *y, const double *informatio
   AB_TRY(require_usable(f));
   timings_reset(h);
   return gp_cv_impl(h, f, y, information, indices, offsets, ngroups, what, 0, 1, mean, var, joint,
-                    score);
+                    score, nullptr);
+}
+
+int ab_gp_cv_scores(ab_handle h, ab_factor f, const double *y, const double *information,
+                    const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+                    double *mean, double *var, double *joint, double *score,
+                    double *group_scores) {
+  AB_REQUIRE(h != nullptr && y != nullptr && information != nullptr && indices != nullptr &&
+                 offsets != nullptr && mean != nullptr && ngroups >= 0,
+             "null");
+  AB_REQUIRE(what == AB_PREDICT_MEAN || (what == AB_PREDICT_MARGINAL && var != nullptr) ||
+                 (what == AB_PREDICT_JOINT && joint != nullptr),
+             "prediction kind / outputs");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  timings_reset(h);
+  return gp_cv_impl(h, f, y, information, indices, offsets, ngroups, what, 0, 1, mean, var, joint,
+                    score, group_scores);
 }
 
 int ab_gp_cv_shard(ab_handle h, ab_factor f, const double *y, const double *information,
@@ -910,10 +961,10 @@ int ab_gp_cv_shard(ab_handle h, ab_factor f, const double *y, const double *info
   // change the partition), so run it as "stride = nshards" with a guard for the degenerate case
   if (nshards == 1) {
     return gp_cv_impl(h, f, y, information, indices, offsets, ngroups, what, 0, 1, mean, var,
-                      nullptr, score);
+                      nullptr, score, nullptr);
   }
   return gp_cv_impl(h, f, y, information, indices, offsets, ngroups, what, shard, nshards, mean,
-                    var, nullptr, score);
+                    var, nullptr, score, nullptr);
 }
 
 // ---- dense building block ---------------------------------------------------------------------

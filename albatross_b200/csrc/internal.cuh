@@ -29,7 +29,8 @@ int64_t dist_total(ab_handle_s *h, int64_t local);
 // Shared implementation of ab_gp_cv / ab_dist_gp_cv (gp.cu).
 int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *information,
                const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
-               int phase, int stride, double *mean, double *var, double *joint, double *score);
+               int phase, int stride, double *mean, double *var, double *joint, double *score,
+               double *group_scores);
 
 // RAII for temporaries so that every early return recycles device buffers.
 struct Scope {

@@ -3,7 +3,7 @@
  *
  * This is the drop-in boundary.  The reference (swift-nav/albatross) has no FFI:
  * its "operator API" is a set of C++ template concepts.  The C++ trait layer shipped in
- * albatross_b200/include/albatross/ re-creates those concepts (same names and signatures) and calls
+ * include/albatross_b200/ (umbrella header albatross.hpp) re-creates those concepts (same names and signatures) and calls
  * ONLY the functions below; INTEGRATION.md shows the binding a reference maintainer would add.
  * Each entry point cites the reference routine it replaces; paths are relative to the reference
  * root, `src/` = include/albatross/src/.
@@ -229,6 +229,16 @@ AB_API int ab_gp_predict(ab_handle h, ab_factor factor, const ab_op *prog, int n
                   const double *test_feats, int64_t p, int what, double *mean, double *var,
                   double *cov);
 /*
+ * ab_gp_predict with separate programs for the cross covariance k(train, test) and the prior
+ * k(test, test).  The two differ when exactly one side of the cross call is a Measurement<> and the
+ * tree holds a MeasurementOnly term (src/covariance_functions/measurement.hpp:70-114), e.g.
+ * fit_model.predict_with_measurement_noise(x) (src/core/fit_model.hpp:54-62).
+ */
+AB_API int ab_gp_predict2(ab_handle h, ab_factor factor, const ab_op *cross_prog, int cross_nops,
+                   const ab_op *prior_prog, int prior_nops, const double *train_feats, int64_t n,
+                   int dim, const double *information, const double *test_feats, int64_t p, int what,
+                   double *mean, double *var, double *cov);
+/*
  * Leave-one-group-out predictions from an existing fit.  Replaces
  * details::held_out_predictions src/evaluation/cross_validation_utils.hpp:199-232 ->
  * held_out_prediction :172-197, scattered back by index (concatenate_*_predictions :59-100).
@@ -239,6 +249,16 @@ AB_API int ab_gp_predict(ab_handle h, ab_factor factor, const ab_op *prog, int n
 AB_API int ab_gp_cv(ab_handle h, ab_factor factor, const double *y, const double *information,
              const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
              double *mean, double *var, double *joint, double *score);
+
+/*
+ * ab_gp_cv that also returns one score per group (group_scores[ngroups], key order; optional): what
+ * CrossValidation::scores(NegativeLogLikelihood<JointDistribution>, dataset, indexer) returns
+ * (src/evaluation/cross_validation.hpp:297-325 -> cross_validated_scores
+ * cross_validation_utils.hpp:102-130) for targets without measurement covariance.
+ */
+AB_API int ab_gp_cv_scores(ab_handle h, ab_factor factor, const double *y, const double *information,
+                    const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
+                    double *mean, double *var, double *joint, double *score, double *group_scores);
 
 /*
  * One shard of ab_gp_cv: only the groups g with g % nshards == shard (for pure leave-one-out: the

@@ -77,6 +77,9 @@ def menu_program(cov_id, p):
             [SE, M32, PROD, EXP, CONST, PROD, SUM, NOISE, SUM],
             [p[0], p[1], p[2], p[3], 0, 0, p[4], p[5], p[6], 0, 0, 0, 0, 0, p[7], 0, 0, 0],
         )
+    if cov_id == 10:
+        # SE + measurement_only(NOISE), as seen between two Measurement<> features (the fit)
+        return [SE, NOISE, SUM], [p[0], p[1], p[2], 0.0, 0.0, 0.0]
     raise ValueError(cov_id)
 
 
@@ -268,7 +271,7 @@ class Ref:
         y = np.ascontiguousarray(y, dtype=np.float64)
         yv = None if yvar is None else np.ascontiguousarray(yvar, dtype=np.float64)
         mean = np.empty(pn)
-        var = np.empty(pn) if what == 1 else None
+        var = np.empty(pn) if what in (1, 5) else None  # 5 = predict_with_measurement_noise marginal
         cov = np.empty((pn, pn), order="F") if what == 2 else None
         rc = cls.lib().ref_gp_predict(C.c_int(cov_id), _d(p), _d(x), C.c_int64(n), C.c_int(dim),
                                       _d(y), _d(yv), _d(t), C.c_int64(pn), C.c_int(what), _d(mean),

@@ -20,6 +20,7 @@
  *   7   SE + Matern52           (BASELINE config 2)       [l1, s1, l2, s2]
  *   8   SE + Matern52 + IndependentNoise                  [l1, s1, l2, s2, sn]
  *   9   SE*Matern32 + Exponential*Constant + Noise        [l1, s1, l2, s2, l3, s3, sc, sn]
+ *   10  SE + measurement_only(IndependentNoise<X>)        [l, s, sn]   (examples/sinc_example.cc:79-80)
  *
  * Feature types: dim==1 -> double, dim==3 -> Eigen::Vector3d, otherwise Eigen::VectorXd
  * (AoS doubles, point i at feats[i*dim .. i*dim+dim)).
@@ -120,6 +121,9 @@ inline int with_cov(int cov_id, const double *p, F &&f) {
     f(SE(p[0], p[1]) * M32(p[2], p[3]) + EXP(p[4], p[5]) * Constant(p[6]) +
       IndependentNoise<X>(p[7]));
     return 0;
+  case 10:
+    f(SE(p[0], p[1]) + albatross::measurement_only(IndependentNoise<X>(p[2])));
+    return 0;
   default:
     return -1;
   }
@@ -138,6 +142,9 @@ inline int with_gp_cov(int cov_id, const double *p, F &&f) {
   case 9:
     f(SE(p[0], p[1]) * M32(p[2], p[3]) + EXP(p[4], p[5]) * Constant(p[6]) +
       IndependentNoise<X>(p[7]));
+    return 0;
+  case 10:
+    f(SE(p[0], p[1]) + albatross::measurement_only(IndependentNoise<X>(p[2])));
     return 0;
   default:
     return -1;

@@ -68,7 +68,8 @@ REF_API int ref_gp_fit(int cov_id, const double *params, const double *feats, in
 }
 
 /*
- * model.fit(dataset).predict(test).{mean,marginal,joint}().  what: 0 mean, 1 marginal, 2 joint.
+ * model.fit(dataset).predict(test).{mean,marginal,joint}().  what: 0 mean, 1 marginal, 2 joint,
+ * 5 (= 1 | 4) marginal of predict_with_measurement_noise(test).
  * mean_out: p ; var_out: p (marginal) ; cov_out: p*p (joint).
  */
 REF_API int ref_gp_predict(int cov_id, const double *params, const double *feats, int64_t n,
@@ -82,6 +83,13 @@ REF_API int ref_gp_predict(int cov_id, const double *params, const double *feats
     return with_gp_cov<X>(cov_id, params, [&](const auto &cov) {
       const auto model = albatross::gp_from_covariance(cov, "oracle");
       const auto fit_model = model.fit(dataset);
+      if (what & 4) { // fit_model.predict_with_measurement_noise(test), fit_model.hpp:54-62
+        const albatross::MarginalDistribution m =
+            fit_model.predict_with_measurement_noise(test_features).marginal();
+        copy_out(m.mean, mean_out);
+        copy_out(Eigen::VectorXd(m.covariance.diagonal()), var_out);
+        return;
+      }
       const auto prediction = fit_model.predict(test_features);
       if (what == 0) {
         copy_out(prediction.mean(), mean_out);

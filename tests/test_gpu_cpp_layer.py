@@ -1,0 +1,203 @@
+"""GPU parity of the C++ trait layer: tests/cpp/trait_layer_check.cc uses the layer exactly as a
+reference user writes code (gp_from_covariance, fit, predict().marginal(), log_likelihood,
+cross_validate(), sparse_gp_from_covariance, DeviceLDLT) and dumps inputs + results; here they are
+compared with the compiled reference (oracle/_ref) run on the very same inputs.
+Tolerances: 1e-9 relative for means / information / likelihoods (north_star), 1e-8 relative to the
+prior scale for variances (formed by cancellation in the reference as well), 4e-15 for Gram entries."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Ref, Restate
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "trait_layer_check")
+RTOL = 1e-9
+
+
+def _parse(path):
+    out = {}
+    with open(path) as fh:
+        while True:
+            head = fh.readline()
+            if not head:
+                break
+            key, count = head.split()
+            out[key] = np.array([float(fh.readline()) for _ in range(int(count))])
+    return out
+
+
+@pytest.fixture(scope="module")
+def dumped(tmp_path_factory):
+    if not os.path.exists(EXE):
+        pytest.fail("tests/cpp/trait_layer_check missing: run __graft_entry__.build()")
+    path = str(tmp_path_factory.mktemp("cpp") / "out.txt")
+    res = subprocess.run([EXE, "gpu", path], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+    d = _parse(path)
+    assert d["kernel_launches"][0] > 0
+    return d
+
+
+SINC = (6, [3.5, 5.7, 1.0])
+
+
+def test_sinc_fit_predict_nll(dumped):
+    d = dumped
+    x, y = d["sinc.x"], d["sinc.y"]
+    cid, p = SINC
+    assert_close(d["sinc.information"], Ref.gp_fit(cid, p, x, y)["information"], RTOL, "information")
+    mean, var, _ = Ref.gp_predict(cid, p, x, y, d["sinc.grid"], 1)
+    assert_close(d["sinc.predict.mean"], mean, RTOL, "mean()")
+    assert_close(d["sinc.predict.marginal.mean"], mean, RTOL, "marginal().mean")
+    assert np.max(np.abs(d["sinc.predict.marginal.var"] - var)) <= 1e-8 * (5.7 ** 2 + 1.0)
+    mean, _, cov = Ref.gp_predict(cid, p, x, y, d["sinc.few"], 2)
+    assert_close(d["sinc.predict.joint.mean"], mean, RTOL, "joint().mean")
+    assert np.max(np.abs(d["sinc.predict.joint.cov"].reshape(5, 5).T - cov)) <= 1e-8 * (5.7 ** 2 + 1.0)
+    nll, _ = Ref.gp_nll(cid, p, x, y)
+    assert abs(d["sinc.nll"][0] - nll) <= RTOL * abs(nll)
+    nll, _ = Ref.gp_nll(cid, [2.0, 5.7, 0.5], x, y)
+    assert abs(d["sinc.tuned.nll"][0] - nll) <= RTOL * abs(nll), "set_param_value must be live"
+
+
+def test_sinc_leave_one_out(dumped):
+    d = dumped
+    x, y = d["sinc.x"], d["sinc.y"]
+    cid, p = SINC
+    mean, var, _, score = Ref.gp_cv(cid, p, x, y, 0, what=1, want_score=True)
+    assert_close(d["sinc.loo.marginal.mean"], mean, RTOL, "LOO mean")
+    assert_close(d["sinc.loo.mean"], mean, RTOL, "LOO mean()")
+    assert_close(d["sinc.loo.marginal.var"], var, 1e-8, "LOO variance")
+    # LeaveOneOutLikelihood<> = sum of per-point joint NLLs - prior ll (prior ll = 0 for these priors)
+    assert abs(d["sinc.loo.likelihood"][0] - score) <= RTOL * abs(score)
+    assert abs(d["sinc.loo.likelihood_marginal"][0] - score) <= RTOL * abs(score)
+    rmse = np.sqrt((mean - y) ** 2)  # per-fold RMSE of one point = |error|; LeaveOneOutRMSE = their mean
+    assert abs(d["sinc.loo.rmse"][0] - rmse.mean()) <= RTOL * rmse.mean()
+
+
+def test_sinc_grouped_cross_validation(dumped):
+    d = dumped
+    x, y = d["sinc.x"], d["sinc.y"]
+    cid, p = SINC
+    sizes = d["sinc.cv.sizes"].astype(int)
+    # integer contract: keys ascending, indices in encounter order, exactly the reference's indexer
+    keys, offsets, indices = Ref.group_indexers(x.reshape(-1, 1), 1, 8.0)
+    assert np.array_equal(d["sinc.cv.keys"].astype(np.int64), keys)
+    assert np.array_equal(d["sinc.cv.indices"].astype(np.int64), indices)
+    assert np.array_equal(sizes, np.diff(offsets))
+    mean, var, _, _ = Ref.gp_cv(cid, p, x, y, 1, 8.0, what=1)
+    assert_close(d["sinc.cv.marginal.mean"], mean, RTOL, "grouped mean")
+    assert_close(d["sinc.cv.marginal.var"], var, 1e-8, "grouped variance")
+    mean2, _, joint, score = Ref.gp_cv(cid, p, x, y, 1, 8.0, what=2, group_sizes=sizes, want_score=True)
+    assert_close(d["sinc.cv.joint_blocks"], joint, 1e-8, "joint blocks")
+    assert_close(d["sinc.cv.group_means"], mean2[indices], RTOL, "group means")
+    # per-group scores = the reference's negative_log_likelihood(joint_g - truth_g)
+    at, want = 0, []
+    for g, k in enumerate(sizes):
+        idx = indices[offsets[g]:offsets[g + 1]]
+        cov = joint[at:at + k * k].reshape(k, k).T
+        at += k * k
+        want.append(Ref.nll_dense(mean2[idx] - y[idx], cov))
+    assert_close(d["sinc.cv.scores"], np.array(want), 1e-8, "scores()")
+    assert abs(d["sinc.cv.scores"].sum() - score) <= 1e-8 * abs(score)
+    assert abs(d["sinc.cv.logo_likelihood"][0] - score) <= 1e-8 * abs(score)
+
+
+def test_sinc_targets_with_measurement_variance(dumped):
+    d = dumped
+    x, y, yvar = d["sinc.x"], d["sinc.y"], d["sinc.yvar"]
+    cid, p = SINC
+    assert_close(d["sinc.noisy.information"], Ref.gp_fit(cid, p, x, y, yvar=yvar)["information"], RTOL)
+    # held-out == brute-force refit (tests/test_cross_validation.cc:156-321), two of the groups
+    keys, offsets, indices = Ref.group_indexers(x.reshape(-1, 1), 1, 8.0)
+    for g in (0, len(keys) - 1):
+        held = indices[offsets[g]:offsets[g + 1]]
+        keep = np.setdiff1d(np.arange(len(x)), held)
+        mean, _, cov = Ref.gp_predict(cid, p, x[keep], y[keep], x[held], 2, yvar=yvar[keep])
+        want = Ref.nll_dense(mean - y[held], cov + np.diag(yvar[held]))
+        assert abs(d["sinc.noisy.scores"][g] - want) <= 1e-7 * abs(want), (g, d["sinc.noisy.scores"][g], want)
+
+
+def test_measurement_only(dumped):
+    d = dumped
+    x, y, t = d["meas.x"], d["meas.y"], d["meas.test"]
+    p = [1.5, 2.0, 0.3]
+    assert_close(d["meas.information"], Ref.gp_fit(10, p, x, y)["information"], RTOL, "information")
+    mean, var, _ = Ref.gp_predict(10, p, x, y, t, 1)
+    assert_close(d["meas.predict.marginal.mean"], mean, RTOL)
+    assert np.max(np.abs(d["meas.predict.marginal.var"] - var)) <= 1e-8 * 4.0
+    mean, _, cov = Ref.gp_predict(10, p, x, y, t, 2)
+    assert np.max(np.abs(d["meas.predict.joint.cov"].reshape(5, 5).T - cov)) <= 1e-8 * 4.0
+    mean, var, _ = Ref.gp_predict(10, p, x, y, t, 5)  # predict_with_measurement_noise
+    assert_close(d["meas.predict_with_noise.marginal.mean"], mean, RTOL)
+    assert np.max(np.abs(d["meas.predict_with_noise.marginal.var"] - var)) <= 1e-8 * 4.0
+    # the noise term is present only between measurements
+    assert np.all(d["meas.predict_with_noise.marginal.var"] - d["meas.predict.marginal.var"] > 0.08)
+    nll, _ = Ref.gp_nll(10, p, x, y)
+    assert abs(d["meas.nll"][0] - nll) <= RTOL * abs(nll)
+
+
+def test_3d_gram_and_gp(dumped):
+    d = dumped
+    x = d["v3.x"].reshape(-1, 3)
+    n = len(x)
+    p7, p8 = [2.0, 1.5, 3.0, 0.7], [2.0, 1.5, 3.0, 0.7, 0.1]
+    K = Ref.gram_sym(7, p7, x)
+    got = d["v3.gram"].reshape(n, n).T
+    assert np.max(np.abs(got - K) / K) <= 4e-15
+    assert np.array_equal(got, got.T)
+    assert_close(d["v3.cross"].reshape(50, n).T, Ref.gram_cross(7, p7, x, x[:50]), 4e-15, "cross")
+    assert_close(d["v3.diag"], Ref.gram_diag(7, p7, x), 4e-15, "diagonal")
+    assert abs(d["v3.scalar"][0] - K[0, 1]) <= 4e-15 * K[0, 1]
+    y = d["v3.y"]
+    assert_close(d["v3.information"], Ref.gp_fit(8, p8, x, y)["information"], RTOL, "information")
+    t = d["v3.test"].reshape(-1, 3)
+    mean, _, cov = Ref.gp_predict(8, p8, x, y, t, 2)
+    assert_close(d["v3.predict.joint.mean"], mean, RTOL)
+    assert np.max(np.abs(d["v3.predict.joint.cov"].reshape(10, 10).T - cov)) <= 1e-8 * 2.75
+    nll, _ = Ref.gp_nll(8, p8, x, y)
+    assert abs(d["v3.nll"][0] - nll) <= RTOL * abs(nll)
+    p9 = [2.0, 1.5, 3.0, 0.7, 1.5, 0.9, 1.1, 0.2]
+    want = Ref.gram_sym(9, p9, x[:, 0])
+    assert_close(d["sop.gram"].reshape(n, n).T, want, 4e-15, "sum of products")
+
+
+def test_device_ldlt_surface(dumped):
+    d = dumped
+    n = 600
+    K = d["ldlt.K"].reshape(n, n).T
+    rhs = d["ldlt.rhs"].reshape(3, n).T
+    want = Ref.ldlt(K, rhs=rhs, want_inverse_diagonal=True)
+    assert_close(d["ldlt.solve"].reshape(3, n).T, want["solve"], RTOL, "solve")
+    s = d["ldlt.sqrt_solve"].reshape(3, n).T
+    assert_close(s.T @ s, rhs.T @ want["solve"], RTOL, "sqrt_solve identity")
+    assert abs(d["ldlt.logdet"][0] - want["logdet"]) <= RTOL * abs(want["logdet"])
+    assert_close(d["ldlt.inverse_diagonal"], want["inverse_diagonal"], RTOL, "inverse_diagonal")
+    groups = [[0, 5, 9], [17], [400, 2, 3, 599]]
+    blocks = Ref.inverse_blocks(K, groups)
+    assert_close(d["ldlt.inverse_blocks"], np.concatenate([b.T.ravel() for b in blocks]), RTOL, "blocks")
+    LD = d["ldlt.packed"].reshape(n, n).T
+    L = np.tril(LD, -1) + np.eye(n)
+    assert_close((L * np.diag(LD)) @ L.T, K, 1e-12, "L D L^T")
+
+
+def test_sparse_gp(dumped):
+    d = dumped
+    x, y, t = d["sparse.x"], d["sparse.y"], d["sparse.test"]
+    p = [1.0, 1.0, 0.1]
+    u = Ref.uniform_inducing_points(x, 48)
+    assert np.array_equal(d["sparse.inducing"], u)  # bit-exact: same accumulation as linspace
+    want = Ref.sparse_gp(6, p, x, y, u, 0, test=t, what=1, want_ll=True)
+    assert_close(d["sparse.fitc.marginal.mean"], want["mean"], RTOL, "FITC mean")
+    assert np.max(np.abs(d["sparse.fitc.marginal.var"] - want["var"])) <= 1e-8
+    assert abs(d["sparse.fitc.ll"][0] - want["ll"]) <= RTOL * abs(want["ll"])
+    wj = Ref.sparse_gp(6, p, x, y, u, 0, test=t, what=2)
+    assert np.max(np.abs(d["sparse.fitc.joint.cov"].reshape(19, 19).T - wj["cov"])) <= 1e-8
+    want = Ref.sparse_gp(6, p, x, y, u, 2, 2.0, test=t, what=1, want_ll=True)
+    assert_close(d["sparse.pitc.marginal.mean"], want["mean"], RTOL, "PITC mean")
+    assert np.max(np.abs(d["sparse.pitc.marginal.var"] - want["var"])) <= 1e-8
+    assert abs(d["sparse.pitc.ll"][0] - want["ll"]) <= RTOL * abs(want["ll"])
