@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libalbatross_b200.so")
+# ALBATROSS_B200_LIB: development aid (tools/sweep.sh loads differently-tuned builds of the library)
+LIB_PATH = os.environ.get("ALBATROSS_B200_LIB") or os.path.join(HERE, "csrc", "libalbatross_b200.so")
 
 # opcodes (include/albatross_b200.h)
 SE, EXP, M32, M52, CONST, NOISE, SUM, PROD = 1, 2, 3, 4, 5, 6, 7, 8

@@ -109,6 +109,9 @@ struct ab_handle_s {
   int rank = 0;
   int world = 1;
   cudaStream_t comm_stream = nullptr; // high-priority stream for panel broadcasts
+  // single-GPU look-ahead factorisation (linalg.cu): panel chain on a high-priority stream
+  cudaStream_t panel_stream = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_col = nullptr;
   cudaEvent_t ev_bcast[2] = {nullptr, nullptr};
   cudaEvent_t ev_ready = nullptr, ev_free = nullptr;
 };

@@ -14,15 +14,48 @@
 
 namespace ab {
 
-constexpr int BM = 128;
-constexpr int BN = 128;
-constexpr int BK = 16;
-constexpr int STAGES = 3;
-constexpr int GEMM_THREADS = 256;
-constexpr int LDMN = BM + 4; // [BK][LDMN] tile of an operand whose m/n index is contiguous in memory
-constexpr int LDK = BK + 4;  // [BM][LDK]  tile of an operand whose k index is contiguous in memory
-constexpr int TILE_MN_ELEMS = BK * LDMN;
-constexpr int TILE_K_ELEMS = BM * LDK;
+// Tile configuration (overridable at compile time for tools/gemm_sweep.sh; the defaults are the
+// measured best).  CTA tile BM x BN x BK, WARPS_M x WARPS_N warps, each owning a
+// (BM / WARPS_M) x (BN / WARPS_N) patch as 8 x 8 DMMA fragments.
+#ifndef AB_GEMM_BM
+#define AB_GEMM_BM 128
+#endif
+#ifndef AB_GEMM_BN
+#define AB_GEMM_BN 128
+#endif
+#ifndef AB_GEMM_BK
+#define AB_GEMM_BK 16
+#endif
+#ifndef AB_GEMM_STAGES
+#define AB_GEMM_STAGES 3
+#endif
+#ifndef AB_GEMM_WARPS_M
+#define AB_GEMM_WARPS_M 2
+#endif
+#ifndef AB_GEMM_WARPS_N
+#define AB_GEMM_WARPS_N 4
+#endif
+#ifndef AB_GEMM_MIN_CTAS
+#define AB_GEMM_MIN_CTAS 1
+#endif
+constexpr int BM = AB_GEMM_BM;
+constexpr int BN = AB_GEMM_BN;
+constexpr int BK = AB_GEMM_BK;
+constexpr int STAGES = AB_GEMM_STAGES;
+constexpr int WARPS_M = AB_GEMM_WARPS_M;
+constexpr int WARPS_N = AB_GEMM_WARPS_N;
+constexpr int GEMM_THREADS = 32 * WARPS_M * WARPS_N;
+constexpr int WTM = BM / WARPS_M; // warp tile
+constexpr int WTN = BN / WARPS_N;
+constexpr int MF = WTM / 8;       // fragments per warp along m / n
+constexpr int NF = WTN / 8;
+static_assert(BM % (8 * WARPS_M) == 0 && BN % (8 * WARPS_N) == 0 && BK % 4 == 0, "tile shape");
+static_assert((BK * BM / 2) % GEMM_THREADS == 0 && (BK * BN / 2) % GEMM_THREADS == 0, "loader shape");
+constexpr int LDK = BK + 4; // [extent][LDK] tile of an operand whose k index is contiguous in memory
+// [BK][extent + 4] tile of an operand whose m/n index is contiguous in memory
+template <int EXTENT, bool KMAJOR> constexpr int tile_elems() {
+  return KMAJOR ? EXTENT * LDK : BK * (EXTENT + 4);
+}
 
 __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc, int src_bytes) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
@@ -46,26 +79,26 @@ __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, doubl
 }
 
 // Loads one BK-deep tile of an operand into shared memory.
-//   KMAJOR == false: element (i, kk) at g[i + kk * ld]   -> smem[kk * LDMN + i]
+//   KMAJOR == false: element (i, kk) at g[i + kk * ld]   -> smem[kk * (EXT + 4) + i]
 //   KMAJOR == true : element (i, kk) at g[kk + i * ld]   -> smem[i * LDK + kk]
-// i in [0, BM) relative to the tile; rows >= extent and k >= kextent are zero-filled (rows beyond
+// i in [0, EXT) relative to the tile; rows >= extent and k >= kextent are zero-filled (rows beyond
 // the extent only ever feed outputs that are not stored, but k beyond kextent must contribute 0).
 // vec == false: the operand is only 8-byte aligned (odd row offset of a sub-view or odd leading
 // dimension): the same chunks are moved as two predicated 8-byte copies.
-template <bool KMAJOR>
+template <int EXT, bool KMAJOR>
 __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t ld, int64_t i0,
                                           int64_t extent, int64_t k0, int64_t kextent, int tid,
                                           bool vec) {
   if (!vec) {
 #pragma unroll
-    for (int it = 0; it < (BK * BM / 2) / GEMM_THREADS; ++it) {
+    for (int it = 0; it < (BK * EXT / 2) / GEMM_THREADS; ++it) {
       const int chunk = tid + it * GEMM_THREADS;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         int i, kk;
         if (!KMAJOR) {
-          kk = chunk / (BM / 2);
-          i = (chunk % (BM / 2)) * 2 + e;
+          kk = chunk / (EXT / 2);
+          i = (chunk % (EXT / 2)) * 2 + e;
         } else {
           i = chunk / (BK / 2);
           kk = (chunk % (BK / 2)) * 2 + e;
@@ -73,24 +106,24 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t
         const bool ok = (i0 + i < extent) && (k0 + kk < kextent);
         const double *src =
             ok ? (KMAJOR ? g + (k0 + kk) + (i0 + i) * ld : g + (i0 + i) + (k0 + kk) * ld) : g;
-        cp_async8(KMAJOR ? smem + i * LDK + kk : smem + kk * LDMN + i, src, ok ? 8 : 0);
+        cp_async8(KMAJOR ? smem + i * LDK + kk : smem + kk * (EXT + 4) + i, src, ok ? 8 : 0);
       }
     }
     return;
   }
   if (!KMAJOR) {
 #pragma unroll
-    for (int it = 0; it < (BK * BM / 2) / GEMM_THREADS; ++it) {
+    for (int it = 0; it < (BK * EXT / 2) / GEMM_THREADS; ++it) {
       const int chunk = tid + it * GEMM_THREADS;
-      const int kk = chunk / (BM / 2);
-      const int ic = (chunk % (BM / 2)) * 2;
+      const int kk = chunk / (EXT / 2);
+      const int ic = (chunk % (EXT / 2)) * 2;
       const bool ok = (i0 + ic < extent) && (k0 + kk < kextent);
       const double *src = ok ? g + (i0 + ic) + (k0 + kk) * ld : g;
-      cp_async16(smem + kk * LDMN + ic, src, ok ? 16 : 0);
+      cp_async16(smem + kk * (EXT + 4) + ic, src, ok ? 16 : 0);
     }
   } else {
 #pragma unroll
-    for (int it = 0; it < (BK * BM / 2) / GEMM_THREADS; ++it) {
+    for (int it = 0; it < (BK * EXT / 2) / GEMM_THREADS; ++it) {
       const int chunk = tid + it * GEMM_THREADS;
       const int i = chunk / (BK / 2);
       const int kc = (chunk % (BK / 2)) * 2;
@@ -102,14 +135,14 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t
   }
 }
 
-template <bool KMAJOR>
+template <int EXT, bool KMAJOR>
 __device__ __forceinline__ double frag(const double *smem, int idx, int kk) {
-  return KMAJOR ? smem[idx * LDK + kk] : smem[kk * LDMN + idx];
+  return KMAJOR ? smem[idx * LDK + kk] : smem[kk * (EXT + 4) + idx];
 }
 
 // TA: op(A) = A^T (A stored k x m, k contiguous).  TB: op(B) = B^T (B stored n x k, n contiguous).
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, AB_GEMM_MIN_CTAS)
 gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int64_t lda,
             const double *B, int64_t ldb, double beta, double *C,
             int64_t ldc, int tiles_m, int lower, int vec_flags) {
@@ -118,14 +151,14 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
   const bool b_vec = vec_flags & 4;      // B: 16-byte cp.async
   constexpr bool A_KMAJOR = TA;
   constexpr bool B_KMAJOR = !TB;
-  constexpr int A_ELEMS = A_KMAJOR ? TILE_K_ELEMS : TILE_MN_ELEMS;
-  constexpr int B_ELEMS = B_KMAJOR ? TILE_K_ELEMS : TILE_MN_ELEMS;
+  constexpr int A_ELEMS = tile_elems<BM, A_KMAJOR>();
+  constexpr int B_ELEMS = tile_elems<BN, B_KMAJOR>();
   extern __shared__ __align__(16) double smem[];
   double *sA = smem;
   double *sB = smem + STAGES * A_ELEMS;
 
   int64_t bm, bn;
-  if (lower) {
+  if (lower && BM == BN) {
     const int64_t t = blockIdx.x;
     int64_t i = static_cast<int64_t>((sqrt(8. * static_cast<double>(t) + 1.) - 1.) * 0.5);
     while (i * (i + 1) / 2 > t) {
@@ -142,20 +175,23 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
   }
   const int64_t m0 = bm * BM;
   const int64_t n0 = bn * BN;
+  if (BM != BN && lower && m0 + BM <= n0) {
+    return; // rectangular tiles: the full grid is launched, tiles strictly above the diagonal exit
+  }
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int wm = warp & 1;  // 2 warps along m (64 rows each)
-  const int wn = warp >> 1; // 4 warps along n (32 cols each)
+  const int wm = warp % WARPS_M;
+  const int wn = warp / WARPS_M;
   const int lq = lane >> 2; // 0..7
   const int lr = lane & 3;  // 0..3
 
-  double acc[4][8][2];
+  double acc[NF][MF][2];
 #pragma unroll
-  for (int nf = 0; nf < 4; ++nf) {
+  for (int nf = 0; nf < NF; ++nf) {
 #pragma unroll
-    for (int mf = 0; mf < 8; ++mf) {
+    for (int mf = 0; mf < MF; ++mf) {
       acc[nf][mf][0] = 0.;
       acc[nf][mf][1] = 0.;
     }
@@ -165,9 +201,9 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
-      load_tile<A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(s) * BK, k, tid,
+      load_tile<BM, A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(s) * BK, k, tid,
                           a_vec);
-      load_tile<B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(s) * BK, k, tid,
+      load_tile<BN, B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(s) * BK, k, tid,
                           b_vec);
     }
     cp_async_commit();
@@ -180,9 +216,9 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
       const int nt = kt + STAGES - 1;
       if (nt < ktiles) {
         const int s = nt % STAGES;
-        load_tile<A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(nt) * BK, k, tid,
+        load_tile<BM, A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(nt) * BK, k, tid,
                             a_vec);
-        load_tile<B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(nt) * BK, k, tid,
+        load_tile<BN, B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(nt) * BK, k, tid,
                             b_vec);
       }
       cp_async_commit();
@@ -192,19 +228,19 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
 #pragma unroll
     for (int ks = 0; ks < BK / 4; ++ks) {
       const int kk = ks * 4 + lr;
-      double fb[4], fa[8];
+      double fb[NF], fa[MF];
 #pragma unroll
-      for (int nf = 0; nf < 4; ++nf) {
-        fb[nf] = frag<B_KMAJOR>(tB, wn * 32 + nf * 8 + lq, kk);
+      for (int nf = 0; nf < NF; ++nf) {
+        fb[nf] = frag<BN, B_KMAJOR>(tB, wn * WTN + nf * 8 + lq, kk);
       }
 #pragma unroll
-      for (int mf = 0; mf < 8; ++mf) {
-        fa[mf] = frag<A_KMAJOR>(tA, wm * 64 + mf * 8 + lq, kk);
+      for (int mf = 0; mf < MF; ++mf) {
+        fa[mf] = frag<BM, A_KMAJOR>(tA, wm * WTM + mf * 8 + lq, kk);
       }
 #pragma unroll
-      for (int nf = 0; nf < 4; ++nf) {
+      for (int nf = 0; nf < NF; ++nf) {
 #pragma unroll
-        for (int mf = 0; mf < 8; ++mf) {
+        for (int mf = 0; mf < MF; ++mf) {
           dmma_884(acc[nf][mf][0], acc[nf][mf][1], fb[nf], fa[mf]);
         }
       }
@@ -212,16 +248,16 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
   }
   cp_async_wait<0>();
 
-  // epilogue: thread owns C(m0 + wm*64 + mf*8 + 2*lr + {0,1}, n0 + wn*32 + nf*8 + lq)
+  // epilogue: thread owns C(m0 + wm*WTM + mf*8 + 2*lr + {0,1}, n0 + wn*WTN + nf*8 + lq)
 #pragma unroll
-  for (int nf = 0; nf < 4; ++nf) {
-    const int64_t col = n0 + wn * 32 + nf * 8 + lq;
+  for (int nf = 0; nf < NF; ++nf) {
+    const int64_t col = n0 + wn * WTN + nf * 8 + lq;
     if (col >= n) {
       continue;
     }
 #pragma unroll
-    for (int mf = 0; mf < 8; ++mf) {
-      const int64_t row = m0 + wm * 64 + mf * 8 + 2 * lr;
+    for (int mf = 0; mf < MF; ++mf) {
+      const int64_t row = m0 + wm * WTM + mf * 8 + 2 * lr;
       if (row >= m) {
         continue;
       }
@@ -257,8 +293,8 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
 template <bool TA, bool TB>
 static int launch(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, double alpha,
                   MatView A, MatView B, double beta, MatView C) {
-  constexpr int A_ELEMS = TA ? TILE_K_ELEMS : TILE_MN_ELEMS;
-  constexpr int B_ELEMS = !TB ? TILE_K_ELEMS : TILE_MN_ELEMS;
+  constexpr int A_ELEMS = tile_elems<BM, TA>();
+  constexpr int B_ELEMS = tile_elems<BN, !TB>();
   constexpr size_t smem = static_cast<size_t>(STAGES) * (A_ELEMS + B_ELEMS) * sizeof(double);
   static bool configured = false;
   if (!configured) {
@@ -268,7 +304,7 @@ static int launch(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, d
   }
   const int64_t tm = (m + BM - 1) / BM;
   const int64_t tn = (n + BN - 1) / BN;
-  const int64_t tiles = lower ? tm * (tm + 1) / 2 : tm * tn;
+  const int64_t tiles = (lower && BM == BN) ? tm * (tm + 1) / 2 : tm * tn;
   AB_REQUIRE(tiles < (int64_t(1) << 31), "GEMM grid too large");
   const auto aligned16 = [](const MatView &M) {
     return reinterpret_cast<uintptr_t>(M.p) % 16 == 0 && M.ld % 2 == 0;

@@ -5,6 +5,13 @@
 // the two sets of instantiations compile in parallel.
 #include "gram_kernel.cuh"
 
+// overridable for tools/sweep.sh
+#ifndef AB_GRAM_COLS
+#define AB_GRAM_COLS 2
+#endif
+#ifndef AB_GRAM_MINB
+#define AB_GRAM_MINB 2
+#endif
 
 namespace ab {
 namespace {
@@ -38,8 +45,8 @@ void launch_one(ab_handle_s *h, const DevProg &P, const double *fx, int64_t ldfx
                 unsigned tiles, uint32_t flags) {
   // 2 columns per pass (4 pairs in flight per thread) measured faster than 4 for the fixed
   // evaluators: 1.958 ms vs 2.074 ms at N = 32 768, SE + Matern52
-  gram_launch<DIM, SYM, EvalFixed<K0, K1, K2>, 2, 2>(h, P, fx, ldfx, n, fy, ldfy, m, out, ld,
-                                                      tiles_i, tiles, flags);
+  gram_launch<DIM, SYM, EvalFixed<K0, K1, K2>, AB_GRAM_COLS, AB_GRAM_MINB>(
+      h, P, fx, ldfx, n, fy, ldfy, m, out, ld, tiles_i, tiles, flags);
 }
 
 template <int K0, int K1, int K2>

@@ -393,6 +393,15 @@ inline int64_t gram_items(bool sym, int64_t tiles_i, int64_t tiles_j) {
   return nsb * (nsb + 1) / 2 * SB * SB;
 }
 
+// Interior-tile stores.  AB_GRAM_STREAM_STORES (tools/sweep.sh) marks them evict-first.
+template <class T> __device__ __forceinline__ void gram_store(T *dst, const T &v) {
+#ifdef AB_GRAM_STREAM_STORES
+  __stcs(dst, v);
+#else
+  *dst = v;
+#endif
+}
+
 constexpr int FEAT_SLOTS = 2; // TILE * AB_MAX_DIM / GRAM_THREADS feature elements per thread
 
 // This thread's share of the x / y features of tile (I, J), straight from global memory.
@@ -438,8 +447,8 @@ __device__ __forceinline__ void mirror_slice(const double *__restrict__ stage,
     const double *src = stage + lane * LDT + rbase;
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-      dst[0] = src[k];
-      dst[32] = src[32 * LDT + k];
+      gram_store(dst, src[k]);
+      gram_store(dst + 32, src[32 * LDT + k]);
       dst += ld;
     }
   } else {
@@ -596,7 +605,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
         double *dst = out + gi + (j0 + cbase) * ld;
 #pragma unroll
         for (int k = 0; k < COLS; ++k) {
-          *reinterpret_cast<double2 *>(dst) = make_double2(vals[2 * k], vals[2 * k + 1]);
+          gram_store(reinterpret_cast<double2 *>(dst), make_double2(vals[2 * k], vals[2 * k + 1]));
           dst += ld;
         }
       } else {

@@ -8,7 +8,9 @@
 // D = diag(L)^2; see DESIGN.md for the parity argument.
 #include "linalg.cuh"
 
+#include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 namespace ab {
 
@@ -88,6 +90,111 @@ potf2_inv_kernel(double *A, int64_t lda, int nb, double *dinv, int64_t global_of
   }
 }
 
+// Version 2 of the leaf: the block and the growing inverse live in REGISTERS (thread (r, g) owns
+// row r, columns g, g + 4, ..., of both), one barrier per column, no divisions or square roots on
+// the critical path except one reciprocal per column.
+//
+// Right-looking elimination on the unscaled Schur complement S (S_0 = block, symmetric) and on
+// W (W_0 = I), for j = 0..63 with d_j = S_j[j][j]:
+//     S[r][c] -= S[r][j] S[c][j] / d_j      (r > j, c > j)
+//     W[r][c] -= S[r][j] W[j][c] / d_j      (r > j, c <= j)          (forward substitution on I)
+// after which L[r][c] = S[r][c] / sqrt(d_c) and (L^-1)[r][c] = W[r][c] / sqrt(d_r).  Column j of S and
+// row j of W are final when step j starts; they are broadcast through double-buffered shared memory.
+// v1 (three barriers, a serial square root and integer divisions per column, then a 64-thread
+// serial substitution for the inverse) took 92 us per leaf; this one is bounded by 64 x (barrier +
+// LDS + reciprocal + 16 FMA) ~ 6 us.
+__global__ void __launch_bounds__(256)
+potf2_inv_kernel_v2(double *A, int64_t lda, int nb, double *dinv, int64_t global_offset,
+                    int *d_bad) {
+  __shared__ double colbuf[2][LEAF];
+  __shared__ double rowbuf[2][LEAF];
+  __shared__ double dpiv[LEAF];
+  const int tid = threadIdx.x;
+  const int r = tid & (LEAF - 1);
+  const int g = tid >> 6; // 0..3
+  constexpr int NI = LEAF / 4;
+  double S[NI], W[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = g + 4 * i;
+    const int hi = r > c ? r : c;
+    const int lo = r > c ? c : r;
+    double v = (r == c) ? 1. : 0.; // identity padding for ragged blocks
+    if (hi < nb) {
+      v = A[hi + lo * lda];
+    }
+    S[i] = v;
+    W[i] = (r == c) ? 1. : 0.;
+  }
+  if (g == 0) {
+    colbuf[0][r] = S[0];
+  }
+  if (r == 0) {
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      rowbuf[0][g + 4 * i] = W[i];
+    }
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int j = 0; j < LEAF; ++j) {
+    const double *col = colbuf[j & 1];
+    const double *wr = rowbuf[j & 1];
+    const double d = col[j];
+    if (tid == 0) {
+      dpiv[j] = d;
+      if (!(d > 0.) && j < nb) {
+        atomicMin(d_bad, static_cast<int>(global_offset + j));
+      }
+    }
+    if (r > j) {
+      const double lr = col[r] * (1. / d);
+      const int ilo = j >> 2; // columns 4 ilo .. 4 ilo + 3 straddle j
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int c = g + 4 * i;
+        if (i < ilo) {
+          W[i] = fma(-lr, wr[c], W[i]);
+        } else if (i > ilo) {
+          S[i] = fma(-lr, col[c], S[i]);
+        } else if (c > j) {
+          S[i] = fma(-lr, col[c], S[i]);
+        } else {
+          W[i] = fma(-lr, wr[c], W[i]);
+        }
+      }
+    }
+    if (j + 1 < LEAF) {
+      if (g == ((j + 1) & 3)) {
+        colbuf[(j + 1) & 1][r] = S[(j + 1) >> 2];
+      }
+      if (r == j + 1) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          rowbuf[(j + 1) & 1][g + 4 * i] = W[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // rs_c = 1 / sqrt(d_c), reusing colbuf[0]
+  if (tid < LEAF) {
+    colbuf[0][tid] = 1. / sqrt(dpiv[tid]);
+  }
+  __syncthreads();
+  const double rs_r = colbuf[0][r];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = g + 4 * i;
+    if (r >= c && r < nb) {
+      A[r + c * lda] = S[i] * colbuf[0][c];
+    }
+    dinv[r + c * LEAF] = (c <= r) ? W[i] * rs_r : 0.;
+  }
+}
+
 static int64_t split(int64_t n) {
   int64_t n1 = round_up((n + 1) / 2, LEAF);
   if (n1 >= n) {
@@ -158,8 +265,13 @@ static int potrf_rec(ab_handle_s *h, MatView A, int64_t n, double *dinv, int64_t
                                    static_cast<int>(smem)));
       configured = true;
     }
+#ifdef AB_LEAF_V1
     potf2_inv_kernel<<<1, 256, smem, h->stream>>>(A.p, A.ld, static_cast<int>(n), dinv, offset,
                                                   d_bad);
+#else
+    potf2_inv_kernel_v2<<<1, 256, 0, h->stream>>>(A.p, A.ld, static_cast<int>(n), dinv, offset,
+                                                  d_bad);
+#endif
     AB_LAUNCHED(h);
     return AB_OK;
   }
@@ -172,11 +284,107 @@ static int potrf_rec(ab_handle_s *h, MatView A, int64_t n, double *dinv, int64_t
   return potrf_rec(h, A.sub(n1, n1), n2, dinv + (n1 / LEAF) * LEAF * LEAF, offset + n1, d_bad);
 }
 
+// Right-looking blocked Cholesky with look-ahead 1 on two streams.
+//
+// The recursion above keeps every O(n^3) flop in large GEMMs, but its bottom levels are a chain of
+// ~14 000 dependent single-CTA kernels (64 x 64 leaves, 64-wide triangular solves) during which 147
+// of the 148 SMs idle: 10-12 % of the factorisation at N = 65 536 (profiles/r01_ncu_launches_*).
+// Here that chain — factor the nb x nb diagonal block, solve the block column below it — runs on a
+// high-priority stream WHILE the previous panel's trailing DSYRK fills the machine:
+//
+//   step k (panel k already factored, block columns > k hold the updates of panels < k):
+//     S: update block column k+1 with panel k            (two GEMMs, r x nb x nb)
+//     P: wait for it; factor panel k+1                   (leaf / small-GEMM chain, 1-2 % of the SMs)
+//     S: update block columns k+2.. with panel k         (one GEMM_LOWER, (r-nb)^2 x nb)  } concurrent
+//
+// The chain is exposed only for the first panel and once the trailing matrix is too small to cover
+// it (r < ~10 000).  Same flops, same kernels, same results as the recursion to rounding.
+#ifndef AB_POTRF_NB
+#define AB_POTRF_NB 1024
+#endif
+constexpr int64_t LA_NB = AB_POTRF_NB; // panel width (multiple of LEAF)
+constexpr int64_t LA_MIN_N = 4 * LA_NB; // below this the plain recursion is used
+static_assert(LA_NB % LEAF == 0, "panel width");
+
+static int ensure_panel_stream(ab_handle_s *h) {
+  if (h->panel_stream != nullptr) {
+    return AB_OK;
+  }
+  int lo = 0, hi = 0;
+  AB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  AB_CUDA(cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, hi));
+  AB_CUDA(cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
+  AB_CUDA(cudaEventCreateWithFlags(&h->ev_col, cudaEventDisableTiming));
+  return AB_OK;
+}
+
+// Every helper launches on h->stream; the panel chain borrows it for the scope.
+struct StreamScope {
+  StreamScope(ab_handle_s *h, cudaStream_t s) : h_(h), saved_(h->stream) { h->stream = s; }
+  ~StreamScope() { h_->stream = saved_; }
+  ab_handle_s *h_;
+  cudaStream_t saved_;
+};
+
+static int factor_panel(ab_handle_s *h, MatView A, int64_t n, int64_t k0, int64_t w, double *dinv,
+                        int *d_bad) {
+  StreamScope scope(h, h->panel_stream);
+  double *dk = dinv + (k0 / LEAF) * LEAF * LEAF;
+  AB_TRY(potrf_rec(h, A.sub(k0, k0), w, dk, k0, d_bad));
+  const int64_t below = n - k0 - w;
+  if (below > 0) {
+    AB_TRY(trsm_right_lower_T(h, A.sub(k0, k0), dk, w, A.sub(k0 + w, k0), below));
+  }
+  AB_CUDA(cudaEventRecord(h->ev_panel, h->panel_stream));
+  return AB_OK;
+}
+
+static int potrf_lookahead(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad) {
+  AB_TRY(ensure_panel_stream(h));
+  cudaStream_t S = h->stream;
+  // the panel stream starts behind everything already enqueued on S (the Gram build of A)
+  AB_CUDA(cudaEventRecord(h->ev_col, S));
+  AB_CUDA(cudaStreamWaitEvent(h->panel_stream, h->ev_col, 0));
+  int status = factor_panel(h, A, n, 0, std::min(LA_NB, n), dinv, d_bad);
+  for (int64_t k0 = 0; status == AB_OK && k0 + LA_NB < n; k0 += LA_NB) {
+    const int64_t w = LA_NB;
+    const int64_t next = k0 + w;
+    const int64_t wn = std::min(LA_NB, n - next);
+    const int64_t rest = n - next - wn;
+    AB_CUDA(cudaStreamWaitEvent(S, h->ev_panel, 0)); // panel k is factored
+    const MatView Pk = A.sub(next, k0);              // rows next.., the w columns of panel k
+    // block column k+1 first ...
+    status = gemm(h, GEMM_TRANS_B | GEMM_LOWER, wn, wn, w, -1., Pk, Pk, 1., A.sub(next, next));
+    if (status == AB_OK && rest > 0) {
+      status = gemm(h, GEMM_TRANS_B, rest, wn, w, -1., A.sub(next + wn, k0), Pk, 1.,
+                    A.sub(next + wn, next));
+    }
+    if (status != AB_OK) {
+      break;
+    }
+    AB_CUDA(cudaEventRecord(h->ev_col, S));
+    AB_CUDA(cudaStreamWaitEvent(h->panel_stream, h->ev_col, 0));
+    // ... so that its factorisation overlaps the rest of this update
+    status = factor_panel(h, A, n, next, wn, dinv, d_bad);
+    if (status == AB_OK && rest > 0) {
+      const MatView Pr = A.sub(next + wn, k0);
+      status = gemm(h, GEMM_TRANS_B | GEMM_LOWER, rest, rest, w, -1., Pr, Pr, 1.,
+                    A.sub(next + wn, next + wn));
+    }
+  }
+  // S continues only after the last panel; on an error the streams are still joined
+  cudaStreamWaitEvent(S, h->ev_panel, 0);
+  return status;
+}
+
 int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad) {
   if (n <= 0) {
     return AB_OK;
   }
   AB_REQUIRE(n < INT_MAX, "matrix too large");
+  if (n >= LA_MIN_N && std::getenv("AB_POTRF_RECURSIVE") == nullptr) {
+    return potrf_lookahead(h, A, n, dinv, d_bad);
+  }
   return potrf_rec(h, A, n, dinv, 0, d_bad);
 }
 

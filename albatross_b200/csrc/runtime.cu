@@ -230,6 +230,11 @@ int ab_destroy(ab_handle h) {
   if (h->h_stage != nullptr) {
     cudaFreeHost(h->h_stage);
   }
+  if (h->panel_stream != nullptr) {
+    cudaStreamDestroy(h->panel_stream);
+    cudaEventDestroy(h->ev_panel);
+    cudaEventDestroy(h->ev_col);
+  }
   if (h->own_stream) {
     cudaStreamDestroy(h->stream);
   }

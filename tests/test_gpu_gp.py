@@ -217,3 +217,32 @@ def test_large_fit_residual_and_consistency(handle):
     Kinv_diag = np.diag(np.linalg.inv(K))
     assert_close(v, 1.0 / Kinv_diag, 1e-8)
     assert_close(m, y - info / Kinv_diag, 1e-8)
+
+
+@pytest.mark.parametrize("n", [4096, 4097, 6000])
+def test_lookahead_factorisation_matches_recursion(handle, n, monkeypatch):
+    """The two-stream look-ahead schedule (linalg.cu potrf_lookahead, n >= 4096) factors the same
+    matrix as the plain recursion: same L to rounding, L L^T = K, same solve; ragged last panel."""
+    ops, pp = prog(8)
+    x = features(n, 3, n)
+    K = handle.gram_sym(ops, pp, x).download()
+    rhs = np.random.default_rng(n).standard_normal((n, 2))
+    f = handle.potrf(handle.upload(K))
+    LD, _ = f.export_packed()
+    sol = f.solve(rhs)
+    monkeypatch.setenv("AB_POTRF_RECURSIVE", "1")
+    f2 = handle.potrf(handle.upload(K))
+    LD2, _ = f2.export_packed()
+    monkeypatch.delenv("AB_POTRF_RECURSIVE")
+    assert f.is_positive_definite() and f2.is_positive_definite()
+    assert_close(np.tril(LD), np.tril(LD2), 1e-11, "L vs recursion")
+    L = np.tril(LD, -1) + np.eye(n)
+    assert_close((L * np.diag(LD)) @ L.T, K, 1e-12, "L D L^T")
+    assert_close(sol, f2.solve(rhs), 1e-10, "solve")
+    resid = np.linalg.norm(K @ sol - rhs) / (np.linalg.norm(K, 2) * np.linalg.norm(sol))
+    assert resid < 1e-14, resid
+    # a non-positive pivot in a late panel is still reported with its global index
+    Kb = K.copy()
+    Kb[n - 3, n - 3] = -1.0
+    fb = handle.potrf(handle.upload(Kb), allow_not_pd=True)
+    assert not fb.is_positive_definite() and fb.info() == n - 3

@@ -1,0 +1,67 @@
+#!/usr/bin/env bash
+# Development aid: builds differently-tuned variants of the library (only gemm.o / gram_fixed.o are
+# recompiled, with -D overrides) into tools/sweep/ and, with "run", times each on the GPU box.
+#   bash tools/sweep.sh build        (here, no GPU)
+#   bash tools/sweep.sh run [tag]    (under gpurun)
+set -u
+cd "$(dirname "$0")/.."
+CS=albatross_b200/csrc
+NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -DAB_BUILDING"
+OUT=tools/sweep
+# tag : source : defines
+VARIANTS=(
+  "g_128x128x16s3:gemm:"
+  "g_128x128x16s4:gemm:-DAB_GEMM_STAGES=4"
+  "g_128x128x32s3:gemm:-DAB_GEMM_BK=32"
+  "g_64x128x16s3c2:gemm:-DAB_GEMM_BM=64 -DAB_GEMM_MIN_CTAS=2"
+  "g_64x128x16s4c2:gemm:-DAB_GEMM_BM=64 -DAB_GEMM_MIN_CTAS=2 -DAB_GEMM_STAGES=4"
+  "g_128x64x16s3c2:gemm:-DAB_GEMM_BN=64 -DAB_GEMM_WARPS_M=4 -DAB_GEMM_WARPS_N=2 -DAB_GEMM_MIN_CTAS=2"
+  "p_nb1024:linalg:"
+  "p_nb512:linalg:-DAB_POTRF_NB=512"
+  "p_nb2048:linalg:-DAB_POTRF_NB=2048"
+  "p_leafv1:linalg:-DAB_LEAF_V1=1"
+  "k_cols2:gram_fixed:"
+  "k_cols4:gram_fixed:-DAB_GRAM_COLS=4"
+  "k_cols1:gram_fixed:-DAB_GRAM_COLS=1"
+  "k_cols2_cs:gram_fixed:-DAB_GRAM_STREAM_STORES=1"
+)
+SKIP_RUN="${SWEEP_SKIP:-}"
+if [ "${1:-build}" = "build" ]; then
+  make -s -j8 -C $CS || exit 1
+  mkdir -p $OUT
+  for v in "${VARIANTS[@]}"; do
+    IFS=: read -r tag src defs <<< "$v"
+    (
+      $NV $defs -c -o $OUT/$tag.o $CS/$src.cu || exit 1
+      objs=$(ls $CS/build/*.o | grep -v "/$src.o")
+      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/lib_$tag.so $OUT/$tag.o $objs -cudart static -ldl
+      rm -f $OUT/$tag.o
+      echo "built $tag"
+    ) &
+  done
+  wait
+  ls -la $OUT
+  exit 0
+fi
+TAG=${2:-sweep}
+mkdir -p gpurun_out
+LOG=gpurun_out/${TAG}_sweep.txt
+: > $LOG
+for v in "${VARIANTS[@]}"; do
+  IFS=: read -r tag src defs <<< "$v"
+  case " $SKIP_RUN " in *" $tag "*) continue;; esac
+  echo "== $tag ($defs)" | tee -a $LOG
+  if [ "$src" = "linalg" ]; then
+    ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
+    ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | tee -a $LOG
+    if [ "$tag" = "p_nb1024" ]; then
+      AB_POTRF_RECURSIVE=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | sed 's/^/recursive: /' | tee -a $LOG
+    fi
+  elif [ "$src" = "gemm" ]; then
+    ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gemm_bench.py 8 2>&1 | tee -a $LOG
+    ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
+  else
+    ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gram_bench.py 32768 7 3 6 2>&1 | tail -1 | tee -a $LOG
+    ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gram_bench.py 32768 7 3 6 1 2>&1 | tail -1 | tee -a $LOG
+  fi
+done
