@@ -316,7 +316,20 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
 
 // Sum of up to three single leaves with compile-time kinds; arithmetic identical to
 // eval_sop<MODE_SUM / MODE_SUM_NOISE> on the same program (same operations in the same order).
-template <int K0, int K1, int K2, bool BIG = true> struct EvalFixed {
+// AB_GRAM_SMALL_TABLE / AB_GRAM_TABLE_GLOBAL (tools/sweep.sh): trade the 16 KB shared-memory table
+// for two more polynomial terms, or read it through L1 instead, to fit a third CTA per SM.
+#ifdef AB_GRAM_SMALL_TABLE
+constexpr bool FIXED_BIG_TABLE = false;
+#else
+constexpr bool FIXED_BIG_TABLE = true;
+#endif
+#ifdef AB_GRAM_TABLE_GLOBAL
+constexpr bool TABLE_IN_SMEM = false;
+#else
+constexpr bool TABLE_IN_SMEM = true;
+#endif
+
+template <int K0, int K1, int K2, bool BIG = FIXED_BIG_TABLE> struct EvalFixed {
   static constexpr bool NEED_EQ = K0 == LS_NOISE || K1 == LS_NOISE || K2 == LS_NOISE;
   static constexpr int TABLE = BIG ? 2048 : 128;
   __device__ static __forceinline__ const double *table() { return BIG ? EXP_TABLE_BIG : EXP_TABLE; }
@@ -351,7 +364,10 @@ template <int K0, int K1, int K2, bool BIG = true> struct EvalFixed {
 //        Items above the diagonal or beyond the last tile row are skipped.  32-bit arithmetic is
 //        exact: the launcher caps the item count at 2^31.
 //   otherwise column-major over the tiles_i x tiles_j grid (rows fastest: contiguous stores).
-constexpr unsigned SB = 16;
+#ifndef AB_GRAM_SB
+#define AB_GRAM_SB 16
+#endif
+constexpr unsigned SB = AB_GRAM_SB;
 
 template <bool SYM>
 __device__ __forceinline__ bool decode_tile(unsigned t, unsigned tiles_i, unsigned &I, unsigned &J) {
@@ -487,8 +503,9 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   constexpr int STAGE = TILE * LDT;
   // dynamic shared memory (gram_smem_bytes): exp table | x features | y features | 2 x mirror staging
   extern __shared__ __align__(16) double gram_smem[];
-  double *tab = gram_smem;
-  double *xs = tab + EV::TABLE;
+  constexpr int TAB_SMEM = TABLE_IN_SMEM ? EV::TABLE : 0;
+  const double *tab = TABLE_IN_SMEM ? gram_smem : EV::table();
+  double *xs = gram_smem + TAB_SMEM;
   double *ys = xs + TILE * DIM;
   double *stage0 = ys + TILE * DIM;
 
@@ -496,8 +513,8 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int r0 = 2 * lane;
-  for (int idx = tid; idx < EV::TABLE; idx += GRAM_THREADS) {
-    tab[idx] = EV::table()[idx];
+  for (int idx = tid; idx < TAB_SMEM; idx += GRAM_THREADS) {
+    gram_smem[idx] = EV::table()[idx];
   }
   const bool need_dist = DIM != 1 && EV::need_dist(P);
 
@@ -661,7 +678,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
 }
 
 template <int DIM, bool SYM, class EV> constexpr size_t gram_smem_bytes() {
-  return sizeof(double) * (EV::TABLE + 2 * TILE * DIM + (SYM ? 2 * TILE * LDT : 0));
+  return sizeof(double) * ((TABLE_IN_SMEM ? EV::TABLE : 0) + 2 * TILE * DIM + (SYM ? 2 * TILE * LDT : 0));
 }
 
 // Launches the persistent kernel: MINB CTAs per SM (or one per tile when there are fewer tiles).
@@ -677,6 +694,14 @@ inline cudaError_t gram_launch(ab_handle_s *h, const DevProg &P, const double *f
                                          static_cast<int>(smem));
     if (e != cudaSuccess) {
       return e;
+    }
+    if (MINB > 2) { // three CTAs per SM only fit with the maximum shared-memory carveout
+      e = cudaFuncSetAttribute(gram_kernel<DIM, SYM, EV, COLS, MINB>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) {
+        return e;
+      }
     }
     configured = true;
   }

@@ -1,0 +1,79 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot run
+them: the reference's LDLT needs 6.4 h and 96 GiB at N = 65 536).  Everything goes through the C ABI.
+
+  configs[1]  Gram build, N = 32 768, 3-D, SE + Matern52: sampled rows against the oracle, bit-identical
+              mirror, lower-only build identical to the full one where it is defined.
+  configs[2]  exact GP, N = 65 536, 3-D, SE + IndependentNoise: K alpha = y, the NLL assembled from its
+              pieces, and the value the 1-GPU recursion and the 2-GPU block-cyclic factorisation agreed on
+              to 3e-13 (profiles/r01_bench_n65536.json, profiles/r01_bench_2gpu_n65536.json).
+"""
+import numpy as np
+import pytest
+
+from albatross_b200 import capi
+from oracle.oracle import Restate
+from tests.helpers import assert_close, features, prog, targets
+
+pytestmark = pytest.mark.gpu
+
+ULP_TOL = 4e-15   # Gram entries (relative), as in test_gpu_gram.py
+RTOL = 1e-9       # north_star tolerance for information / NLL
+
+
+def test_gram_config2_full_size(handle):
+    n = 32768
+    ops, pp = prog(7)
+    x = features(n, 3, 0)
+    fd = handle.upload_features(x)
+    K = handle.gram_sym_d(ops, pp, fd)
+    assert K.shape == (n, n)
+    rows = [0, 1, 63, 64, 65, 1023, 1024, 16383, 16384, 20000, n - 65, n - 64, n - 1]
+    for r in rows:
+        got = K.download_block(r, 0, 1, n).ravel()
+        want = Restate.gram_cross(ops, pp, x[r:r + 1], x).ravel()
+        assert_close(got, want, ULP_TOL, f"row {r}")
+        col = K.download_block(0, r, n, 1).ravel()
+        assert np.array_equal(col, got), f"mirror of row {r} must be bit-identical"
+    # the lower-only build (what fit uses) writes the same values on and below the diagonal
+    Kl = handle.gram_sym_d(ops, pp, fd, flags=capi.GRAM_LOWER_ONLY)
+    for c0 in (0, 4096, 20032, n - 128):
+        a = K.download_block(c0, c0, n - c0, 64)
+        b = Kl.download_block(c0, c0, n - c0, 64)
+        tri = np.tril(np.ones((n - c0, 64), dtype=bool))
+        assert np.array_equal(a[tri], b[tri]), f"lower-only build differs at column block {c0}"
+    K.free()
+    Kl.free()
+    fd.free()
+
+
+def test_exact_gp_config3_full_size(handle):
+    n = 65536
+    ops, pp = prog(6)
+    x = features(n, 3, 0)
+    y = targets(x)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    assert f.is_positive_definite()
+    assert np.all(np.isfinite(info))
+    # K alpha = y with the independently rebuilt full symmetric K (GEMV on the device)
+    fd = handle.upload_features(x)
+    K = handle.gram_sym_d(ops, pp, fd)
+    a_dev = handle.upload(info)
+    r_dev = handle.alloc(n, 1)
+    handle.gemm(K, a_dev, r_dev)
+    resid = r_dev.download().ravel() - y
+    assert np.linalg.norm(resid) <= RTOL * np.linalg.norm(y), np.linalg.norm(resid) / np.linalg.norm(y)
+    # the diagonal carries sigma_se^2 + sigma_noise^2
+    d = K.download_block(0, 0, 1, 1)[0, 0]
+    assert abs(d - 1.01) <= 4e-16 * 1.01, d
+    K.free()
+    a_dev.free()
+    r_dev.free()
+    fd.free()
+    logdet = f.log_determinant()
+    f.free()
+    # log-likelihood = a second Gram + factorisation (models/gp.hpp:443-451); consistent with the fit
+    nll = handle.gp_nll(ops, pp, x, y)
+    want = 0.5 * (logdet + y @ info + n * np.log(2.0 * np.pi))
+    assert abs(nll - want) <= 1e-10 * abs(want), (nll, want)
+    # value on which the recursive 1-GPU and the block-cyclic 2-GPU factorisations agreed to 3e-13
+    assert abs(nll - (-64227.1208743)) <= RTOL * 64227.0, nll

@@ -10,20 +10,22 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 OUT=tools/sweep
 # tag : source : defines
 VARIANTS=(
-  "g_128x128x16s3:gemm:"
-  "g_128x128x16s4:gemm:-DAB_GEMM_STAGES=4"
-  "g_128x128x32s3:gemm:-DAB_GEMM_BK=32"
-  "g_64x128x16s3c2:gemm:-DAB_GEMM_BM=64 -DAB_GEMM_MIN_CTAS=2"
-  "g_64x128x16s4c2:gemm:-DAB_GEMM_BM=64 -DAB_GEMM_MIN_CTAS=2 -DAB_GEMM_STAGES=4"
-  "g_128x64x16s3c2:gemm:-DAB_GEMM_BN=64 -DAB_GEMM_WARPS_M=4 -DAB_GEMM_WARPS_N=2 -DAB_GEMM_MIN_CTAS=2"
+  "k_cols2:gram_fixed:"
+  "k_tabg_mb3:gram_fixed:-DAB_GRAM_TABLE_GLOBAL=1 -DAB_GRAM_MINB=3"
+  "k_tabg_mb2:gram_fixed:-DAB_GRAM_TABLE_GLOBAL=1"
+  "k_small_mb3:gram_fixed:-DAB_GRAM_SMALL_TABLE=1 -DAB_GRAM_MINB=3"
+  "k_tabg_mb3_cs:gram_fixed:-DAB_GRAM_TABLE_GLOBAL=1 -DAB_GRAM_MINB=3 -DAB_GRAM_STREAM_STORES=1"
+  "k_cols2_cs:gram_fixed:-DAB_GRAM_STREAM_STORES=1"
+  "k_cols4:gram_fixed:-DAB_GRAM_COLS=4"
+  "k_sb8:gram_fixed,gram:-DAB_GRAM_SB=8"
+  "k_sb32:gram_fixed,gram:-DAB_GRAM_SB=32"
   "p_nb1024:linalg:"
   "p_nb512:linalg:-DAB_POTRF_NB=512"
   "p_nb2048:linalg:-DAB_POTRF_NB=2048"
-  "p_leafv1:linalg:-DAB_LEAF_V1=1"
-  "k_cols2:gram_fixed:"
-  "k_cols4:gram_fixed:-DAB_GRAM_COLS=4"
-  "k_cols1:gram_fixed:-DAB_GRAM_COLS=1"
-  "k_cols2_cs:gram_fixed:-DAB_GRAM_STREAM_STORES=1"
+  "g_128x128x16s3:gemm:"
+  "g_128x128x32s3:gemm:-DAB_GEMM_BK=32"
+  "g_64x128x16s3c2:gemm:-DAB_GEMM_BM=64 -DAB_GEMM_MIN_CTAS=2"
+  "g_128x64x16s3c2:gemm:-DAB_GEMM_BN=64 -DAB_GEMM_WARPS_M=4 -DAB_GEMM_WARPS_N=2 -DAB_GEMM_MIN_CTAS=2"
 )
 SKIP_RUN="${SWEEP_SKIP:-}"
 if [ "${1:-build}" = "build" ]; then
@@ -32,10 +34,15 @@ if [ "${1:-build}" = "build" ]; then
   for v in "${VARIANTS[@]}"; do
     IFS=: read -r tag src defs <<< "$v"
     (
-      $NV $defs -c -o $OUT/$tag.o $CS/$src.cu || exit 1
-      objs=$(ls $CS/build/*.o | grep -v "/$src.o")
-      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/lib_$tag.so $OUT/$tag.o $objs -cudart static -ldl
-      rm -f $OUT/$tag.o
+      objs=$(ls $CS/build/*.o)
+      mine=""
+      for one in ${src//,/ }; do
+        $NV $defs -c -o $OUT/${tag}_$one.o $CS/$one.cu || exit 1
+        objs=$(echo "$objs" | grep -v "/$one.o")
+        mine="$mine $OUT/${tag}_$one.o"
+      done
+      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/lib_$tag.so $mine $objs -cudart static -ldl
+      rm -f $mine
       echo "built $tag"
     ) &
   done
@@ -50,7 +57,9 @@ LOG=gpurun_out/${TAG}_sweep.txt
 for v in "${VARIANTS[@]}"; do
   IFS=: read -r tag src defs <<< "$v"
   case " $SKIP_RUN " in *" $tag "*) continue;; esac
+  if [ -n "${SWEEP_ONLY:-}" ]; then case "$tag" in ${SWEEP_ONLY}) ;; *) continue;; esac; fi
   echo "== $tag ($defs)" | tee -a $LOG
+  src=${src%%,*}
   if [ "$src" = "linalg" ]; then
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | tee -a $LOG
