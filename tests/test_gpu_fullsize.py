@@ -22,6 +22,7 @@ RTOL = 1e-9       # north_star tolerance for information / NLL
 
 def test_gram_config2_full_size(handle):
     n = 32768
+    handle.trim()  # release the buffers earlier tests left in the handle's pool
     ops, pp = prog(7)
     x = features(n, 3, 0)
     fd = handle.upload_features(x)
@@ -48,6 +49,7 @@ def test_gram_config2_full_size(handle):
 
 def test_exact_gp_config3_full_size(handle):
     n = 65536
+    handle.trim()
     ops, pp = prog(6)
     x = features(n, 3, 0)
     y = targets(x)

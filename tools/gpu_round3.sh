@@ -25,7 +25,7 @@ leg() { # leg <max seconds> <name> <command...>: skipped when the deadline is to
 }
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 
-leg 600 pytest bash -c "python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/${TAG}_pytest.log"
+leg 600 pytest bash -c "python -m pytest tests -m gpu -q --durations=8 2>&1 | tail -40 | tee $OUT/${TAG}_pytest.log"
 leg 420 bench bash -c "python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; tail -c 2500 $OUT/${TAG}_bench.json"
 leg 120 store_pattern bash -c "tools/store_pattern 32768 2>&1 | tee $OUT/${TAG}_store_pattern.txt"
 leg 300 sweep_gram env SWEEP_ONLY='k_*' bash tools/sweep.sh run ${TAG}_gram
