@@ -21,7 +21,7 @@ namespace ab {
 #define AB_GEMM_BM 128
 #endif
 #ifndef AB_GEMM_BN
-#define AB_GEMM_BN 128
+#define AB_GEMM_BN 64
 #endif
 #ifndef AB_GEMM_BK
 #define AB_GEMM_BK 16
@@ -30,13 +30,13 @@ namespace ab {
 #define AB_GEMM_STAGES 3
 #endif
 #ifndef AB_GEMM_WARPS_M
-#define AB_GEMM_WARPS_M 2
+#define AB_GEMM_WARPS_M 4
 #endif
 #ifndef AB_GEMM_WARPS_N
-#define AB_GEMM_WARPS_N 4
+#define AB_GEMM_WARPS_N 2
 #endif
 #ifndef AB_GEMM_MIN_CTAS
-#define AB_GEMM_MIN_CTAS 1
+#define AB_GEMM_MIN_CTAS 2
 #endif
 constexpr int BM = AB_GEMM_BM;
 constexpr int BN = AB_GEMM_BN;

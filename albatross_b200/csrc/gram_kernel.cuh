@@ -25,7 +25,17 @@
 namespace ab {
 
 constexpr int TILE = 64;
-constexpr int LDT = TILE + 1;
+// Mirror staging buffer, element (c, r) of the tile (column c, row r):
+//   swizzled (default): stage[c * 64 + 2 * ((r >> 1) ^ (c & 7)) + (r & 1)] — 16-byte granules
+//     XOR-swizzled by the column, so that both the producer (lane = row pair, one STS.128 per column)
+//     and the mirror (lane = column, one LDS.128 per row pair) are bank-conflict free;
+//   padded (AB_GRAM_SWIZZLE=0): stage[c * 65 + r], 8-byte accesses (producer 2-way conflicted).
+#ifndef AB_GRAM_SWIZZLE
+#define AB_GRAM_SWIZZLE 1
+#endif
+constexpr bool STAGE_SWIZZLE = AB_GRAM_SWIZZLE != 0;
+constexpr int LDT = STAGE_SWIZZLE ? TILE : TILE + 1;
+__device__ __forceinline__ int stage_granule(int c, int g) { return c * TILE + 2 * (g ^ (c & 7)); }
 constexpr int GRAM_THREADS = 256;
 // A thread owns 2 rows x COLS columns per pass (2 * COLS pairs in flight); 8 / COLS passes cover the
 // 64 columns of the tile.
@@ -75,6 +85,30 @@ __device__ __forceinline__ double exp_core_big(double x, const double *__restric
   return __hiloint2double(__double2hiint(res) + (m & ~2047) * 512, __double2loint(res));
 }
 
+// Same with a 256-entry table held in shared memory in 16 interleaved copies, copy (lane & 15) at
+// tab[16 j + (lane & 15)]: the 16 lanes of a half-warp always hit 16 different 8-byte banks, so the
+// data-dependent lookup costs the minimum two wavefronts.  (The plain 2048-entry table costs ~6:
+// ncu counted 1.6e8 bank-conflict cycles at N = 32 768, 28 % of all SM cycles, with L1/shared the
+// busiest unit of the kernel at 75 %.)  |r| <= ln2/512, degree-4 polynomial, 9 FP64-pipe
+// instructions, relative error <= 2.2 * 2^-53.  `tab_lane` = table base + (lane & 15).
+constexpr int EXP_REPL = 16;
+__device__ __forceinline__ double exp_core_r256(double x, const double *__restrict__ tab_lane,
+                                                int &hi_max) {
+  const double t = fma(x, 369.3299304675746, 6755399441055744.0); // x * 256/ln2
+  const int m = __double2loint(t);
+  const double mf = t - 6755399441055744.0;
+  double r = fma(mf, -0x1.62e42fef00000p-9, x);
+  r = fma(mf, -0x1.473de6af278edp-42, r);
+  double p = fma(r, 0.041666666666666664, 0.16666666666666666);
+  p = fma(p, r, 0.5);
+  const double r2 = r * r;
+  const double q = fma(p, r2, r); // expm1(r)
+  const double tj = tab_lane[(m & 255) * EXP_REPL];
+  const double res = fma(tj, q, tj);
+  hi_max = max(hi_max, __double2hiint(x));
+  return __hiloint2double(__double2hiint(res) + (m & ~255) * 4096, __double2loint(res));
+}
+
 constexpr int EXP_HI_LIMIT = static_cast<int>(0xC0862000u);
 
 __device__ __forceinline__ double exp_patch(double x, double fast) {
@@ -120,13 +154,18 @@ __device__ __forceinline__ double sqrt_patch(double a, double fast) {
 constexpr int MODE_SUM = 0, MODE_SUM_NOISE = 1, MODE_SOP = 2, MODE_STACK = 3;
 
 // exp of NP arguments with one range check for the batch
-template <int NP, bool BIG = false>
+// table kinds: plain 128 entries (degree 5) | plain 2048 entries (degree 3) | 256 entries x 16 copies
+constexpr int TAB_128 = 0, TAB_2048 = 1, TAB_R256 = 2;
+
+template <int NP, int TAB = TAB_128>
 __device__ __forceinline__ void exp_batch(const double (&v)[NP], const double *__restrict__ tab,
                                           double (&e)[NP]) {
   int hi_max = EXP_HI_LIMIT;
 #pragma unroll
   for (int i = 0; i < NP; ++i) {
-    e[i] = BIG ? exp_core_big(v[i], tab, hi_max) : exp_core(v[i], tab, hi_max);
+    e[i] = TAB == TAB_2048   ? exp_core_big(v[i], tab, hi_max)
+           : TAB == TAB_R256 ? exp_core_r256(v[i], tab, hi_max)
+                             : exp_core(v[i], tab, hi_max);
   }
   if (hi_max > EXP_HI_LIMIT) { // rare
 #pragma unroll
@@ -238,8 +277,14 @@ __device__ __noinline__ double eval_stack(const DevProg &P, double d2, double di
 
 template <int MODE> struct EvalProgram {
   static constexpr bool NEED_EQ = MODE != MODE_SUM;
-  static constexpr int TABLE = 128;
+  static constexpr int TABLE = 128; // doubles of shared memory
   __device__ static __forceinline__ const double *table() { return EXP_TABLE; }
+  __device__ static __forceinline__ void fill_table(double *smem, int tid) {
+    for (int idx = tid; idx < TABLE; idx += GRAM_THREADS) {
+      smem[idx] = EXP_TABLE[idx];
+    }
+  }
+  __device__ static __forceinline__ const double *lane_table(const double *smem, int) { return smem; }
   __device__ static __forceinline__ bool need_dist(const DevProg &P) { return P.need_dist != 0; }
   template <int NP>
   __device__ static __forceinline__ void run(const DevProg &P, const double (&d2)[NP],
@@ -259,7 +304,7 @@ template <int MODE> struct EvalProgram {
 // Compile-time leaf kinds of EvalFixed.
 enum LeafSig : int { LS_NONE = 0, LS_SE = 1, LS_EXP = 2, LS_M32 = 3, LS_M52 = 4, LS_CONST = 5, LS_NOISE = 6 };
 
-template <int KIND, int NP, bool BIG>
+template <int KIND, int NP, int TAB>
 __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP],
                                            const double (&dist)[NP], unsigned eqmask,
                                            const double *__restrict__ tab, double (&out)[NP]) {
@@ -292,7 +337,7 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
         v[i] = a1 * dist[i];
       }
     }
-    exp_batch<NP, BIG>(v, tab, e);
+    exp_batch<NP, TAB>(v, tab, e);
     if constexpr (KIND == LS_M32) {
       const double b1 = o.b1;
 #pragma unroll
@@ -316,23 +361,35 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
 
 // Sum of up to three single leaves with compile-time kinds; arithmetic identical to
 // eval_sop<MODE_SUM / MODE_SUM_NOISE> on the same program (same operations in the same order).
-// AB_GRAM_SMALL_TABLE / AB_GRAM_TABLE_GLOBAL (tools/sweep.sh): trade the 16 KB shared-memory table
-// for two more polynomial terms, or read it through L1 instead, to fit a third CTA per SM.
-#ifdef AB_GRAM_SMALL_TABLE
-constexpr bool FIXED_BIG_TABLE = false;
-#else
-constexpr bool FIXED_BIG_TABLE = true;
+// AB_GRAM_TABLE (tools/sweep.sh) selects the table of the fixed evaluators; AB_GRAM_TABLE_GLOBAL
+// reads a plain table through L1 instead of shared memory (measured slower: L1/shared is the
+// kernel's busiest unit).
+#ifndef AB_GRAM_TABLE
+#define AB_GRAM_TABLE 2
 #endif
+constexpr int FIXED_TABLE = AB_GRAM_TABLE;
 #ifdef AB_GRAM_TABLE_GLOBAL
 constexpr bool TABLE_IN_SMEM = false;
+static_assert(AB_GRAM_TABLE != 2, "the replicated table lives in shared memory");
 #else
 constexpr bool TABLE_IN_SMEM = true;
 #endif
 
-template <int K0, int K1, int K2, bool BIG = FIXED_BIG_TABLE> struct EvalFixed {
+template <int K0, int K1, int K2, int TAB = FIXED_TABLE> struct EvalFixed {
   static constexpr bool NEED_EQ = K0 == LS_NOISE || K1 == LS_NOISE || K2 == LS_NOISE;
-  static constexpr int TABLE = BIG ? 2048 : 128;
-  __device__ static __forceinline__ const double *table() { return BIG ? EXP_TABLE_BIG : EXP_TABLE; }
+  static constexpr int TABLE = TAB == TAB_2048 ? 2048 : (TAB == TAB_R256 ? 256 * EXP_REPL : 128);
+  __device__ static __forceinline__ const double *table() {
+    return TAB == TAB_128 ? EXP_TABLE : EXP_TABLE_BIG;
+  }
+  __device__ static __forceinline__ void fill_table(double *smem, int tid) {
+    for (int idx = tid; idx < TABLE; idx += GRAM_THREADS) {
+      // 2^(j/256) = EXP_TABLE_BIG[8 j]
+      smem[idx] = TAB == TAB_R256 ? EXP_TABLE_BIG[(idx / EXP_REPL) * 8] : table()[idx];
+    }
+  }
+  __device__ static __forceinline__ const double *lane_table(const double *smem, int lane) {
+    return TAB == TAB_R256 ? smem + (lane & (EXP_REPL - 1)) : smem;
+  }
   static constexpr bool NEED_DIST = (K0 >= LS_EXP && K0 <= LS_M52) || (K1 >= LS_EXP && K1 <= LS_M52) ||
                                     (K2 >= LS_EXP && K2 <= LS_M52);
   __device__ static __forceinline__ bool need_dist(const DevProg &) { return NEED_DIST; }
@@ -344,9 +401,9 @@ template <int K0, int K1, int K2, bool BIG = FIXED_BIG_TABLE> struct EvalFixed {
     for (int i = 0; i < NP; ++i) {
       out[i] = 0.;
     }
-    fixed_term<K0, NP, BIG>(P.ops[0], d2, dist, eqmask, tab, out);
-    fixed_term<K1, NP, BIG>(P.ops[1], d2, dist, eqmask, tab, out);
-    fixed_term<K2, NP, BIG>(P.ops[2], d2, dist, eqmask, tab, out);
+    fixed_term<K0, NP, TAB>(P.ops[0], d2, dist, eqmask, tab, out);
+    fixed_term<K1, NP, TAB>(P.ops[1], d2, dist, eqmask, tab, out);
+    fixed_term<K2, NP, TAB>(P.ops[2], d2, dist, eqmask, tab, out);
   }
 };
 
@@ -455,9 +512,34 @@ __device__ __forceinline__ void mirror_slice(const double *__restrict__ stage,
                                              unsigned I, unsigned J, bool interior, int part,
                                              int lane, int warp) {
   constexpr int KS = 8 / PARTS;
+  static_assert(!STAGE_SWIZZLE || KS % 2 == 0, "a mirror slice is a whole number of row pairs");
   const int64_t i0 = static_cast<int64_t>(I) * TILE;
   const int64_t j0 = static_cast<int64_t>(J) * TILE;
   const int rbase = warp * 8 + part * KS;
+  if (STAGE_SWIZZLE) {
+#pragma unroll
+    for (int k = 0; k < KS; k += 2) {
+      const int r = rbase + k;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int c = lane + 32 * half;
+        const double2 v = *reinterpret_cast<const double2 *>(stage + stage_granule(c, r >> 1));
+        double *dst = out + (j0 + c) + (i0 + r) * ld;
+        if (interior) {
+          gram_store(dst, v.x);
+          gram_store(dst + ld, v.y);
+        } else if (j0 + c < n) {
+          if (i0 + r < n) {
+            dst[0] = v.x;
+          }
+          if (i0 + r + 1 < n) {
+            dst[ld] = v.y;
+          }
+        }
+      }
+    }
+    return;
+  }
   if (interior) {
     double *dst = out + (j0 + lane) + (i0 + rbase) * ld;
     const double *src = stage + lane * LDT + rbase;
@@ -504,7 +586,6 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   // dynamic shared memory (gram_smem_bytes): exp table | x features | y features | 2 x mirror staging
   extern __shared__ __align__(16) double gram_smem[];
   constexpr int TAB_SMEM = TABLE_IN_SMEM ? EV::TABLE : 0;
-  const double *tab = TABLE_IN_SMEM ? gram_smem : EV::table();
   double *xs = gram_smem + TAB_SMEM;
   double *ys = xs + TILE * DIM;
   double *stage0 = ys + TILE * DIM;
@@ -513,9 +594,10 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   const int lane = tid & 31;
   const int warp = tid >> 5;
   const int r0 = 2 * lane;
-  for (int idx = tid; idx < TAB_SMEM; idx += GRAM_THREADS) {
-    gram_smem[idx] = EV::table()[idx];
+  if (TABLE_IN_SMEM) {
+    EV::fill_table(gram_smem, tid);
   }
+  const double *tab = TABLE_IN_SMEM ? EV::lane_table(gram_smem, lane) : EV::table();
   const bool need_dist = DIM != 1 && EV::need_dist(P);
 
   unsigned t = blockIdx.x;
@@ -647,8 +729,13 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
 #pragma unroll
         for (int k = 0; k < COLS; ++k) {
           const int c = cbase + k;
-          stage[c * LDT + r0] = vals[2 * k];
-          stage[c * LDT + r0 + 1] = vals[2 * k + 1];
+          if (STAGE_SWIZZLE) {
+            *reinterpret_cast<double2 *>(stage + stage_granule(c, lane)) =
+                make_double2(vals[2 * k], vals[2 * k + 1]);
+          } else {
+            stage[c * LDT + r0] = vals[2 * k];
+            stage[c * LDT + r0 + 1] = vals[2 * k + 1];
+          }
         }
       }
       if (SYM && (pend & 1u)) {

@@ -300,7 +300,7 @@ static int potrf_rec(ab_handle_s *h, MatView A, int64_t n, double *dinv, int64_t
 // The chain is exposed only for the first panel and once the trailing matrix is too small to cover
 // it (r < ~10 000).  Same flops, same kernels, same results as the recursion to rounding.
 #ifndef AB_POTRF_NB
-#define AB_POTRF_NB 1024
+#define AB_POTRF_NB 2048
 #endif
 constexpr int64_t LA_NB = AB_POTRF_NB; // panel width (multiple of LEAF)
 constexpr int64_t LA_MIN_N = 4 * LA_NB; // below this the plain recursion is used
@@ -382,7 +382,13 @@ int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad) {
     return AB_OK;
   }
   AB_REQUIRE(n < INT_MAX, "matrix too large");
-  if (n >= LA_MIN_N && std::getenv("AB_POTRF_RECURSIVE") == nullptr) {
+  // AB_POTRF_RECURSIVE / AB_POTRF_LOOKAHEAD_MIN: test hooks (tests/test_gpu_gp.py compares the two
+  // schedules at sizes below the default threshold)
+  int64_t min_n = LA_MIN_N;
+  if (const char *e = std::getenv("AB_POTRF_LOOKAHEAD_MIN")) {
+    min_n = std::atoll(e);
+  }
+  if (n >= min_n && std::getenv("AB_POTRF_RECURSIVE") == nullptr) {
     return potrf_lookahead(h, A, n, dinv, d_bad);
   }
   return potrf_rec(h, A, n, dinv, 0, d_bad);

@@ -221,15 +221,18 @@ def test_large_fit_residual_and_consistency(handle):
 
 @pytest.mark.parametrize("n", [4096, 4097, 6000])
 def test_lookahead_factorisation_matches_recursion(handle, n, monkeypatch):
-    """The two-stream look-ahead schedule (linalg.cu potrf_lookahead, n >= 4096) factors the same
+    """The two-stream look-ahead schedule (linalg.cu potrf_lookahead, panels of 2048) factors the same
     matrix as the plain recursion: same L to rounding, L L^T = K, same solve; ragged last panel."""
     ops, pp = prog(8)
     x = features(n, 3, n)
     K = handle.gram_sym(ops, pp, x).download()
     rhs = np.random.default_rng(n).standard_normal((n, 2))
+    # force the look-ahead schedule at these sizes (default threshold: 4 panels of 2048)
+    monkeypatch.setenv("AB_POTRF_LOOKAHEAD_MIN", "1")
     f = handle.potrf(handle.upload(K))
     LD, _ = f.export_packed()
     sol = f.solve(rhs)
+    monkeypatch.delenv("AB_POTRF_LOOKAHEAD_MIN")
     monkeypatch.setenv("AB_POTRF_RECURSIVE", "1")
     f2 = handle.potrf(handle.upload(K))
     LD2, _ = f2.export_packed()

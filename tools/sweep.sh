@@ -10,22 +10,20 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 OUT=tools/sweep
 # tag : source : defines
 VARIANTS=(
-  "k_cols2:gram_fixed:"
-  "k_tabg_mb3:gram_fixed:-DAB_GRAM_TABLE_GLOBAL=1 -DAB_GRAM_MINB=3"
-  "k_tabg_mb2:gram_fixed:-DAB_GRAM_TABLE_GLOBAL=1"
-  "k_small_mb3:gram_fixed:-DAB_GRAM_SMALL_TABLE=1 -DAB_GRAM_MINB=3"
-  "k_tabg_mb3_cs:gram_fixed:-DAB_GRAM_TABLE_GLOBAL=1 -DAB_GRAM_MINB=3 -DAB_GRAM_STREAM_STORES=1"
-  "k_cols2_cs:gram_fixed:-DAB_GRAM_STREAM_STORES=1"
-  "k_cols4:gram_fixed:-DAB_GRAM_COLS=4"
-  "k_sb8:gram_fixed,gram:-DAB_GRAM_SB=8"
-  "k_sb32:gram_fixed,gram:-DAB_GRAM_SB=32"
-  "p_nb1024:linalg:"
-  "p_nb512:linalg:-DAB_POTRF_NB=512"
-  "p_nb2048:linalg:-DAB_POTRF_NB=2048"
-  "g_128x128x16s3:gemm:"
-  "g_128x128x32s3:gemm:-DAB_GEMM_BK=32"
-  "g_64x128x16s3c2:gemm:-DAB_GEMM_BM=64 -DAB_GEMM_MIN_CTAS=2"
-  "g_128x64x16s3c2:gemm:-DAB_GEMM_BN=64 -DAB_GEMM_WARPS_M=4 -DAB_GEMM_WARPS_N=2 -DAB_GEMM_MIN_CTAS=2"
+  "k_new:gram_fixed:"
+  "k_old:gram_fixed:-DAB_GRAM_TABLE=1 -DAB_GRAM_SWIZZLE=0"
+  "k_r256_pad:gram_fixed:-DAB_GRAM_TABLE=2 -DAB_GRAM_SWIZZLE=0"
+  "k_t2048_swz:gram_fixed:-DAB_GRAM_TABLE=1 -DAB_GRAM_SWIZZLE=1"
+  "k_new_cols4:gram_fixed:-DAB_GRAM_COLS=4"
+  "k_new_cs:gram_fixed:-DAB_GRAM_STREAM_STORES=1"
+  "p_nb2048:linalg:"
+  "p_nb1024:linalg:-DAB_POTRF_NB=1024"
+  "p_nb3072:linalg:-DAB_POTRF_NB=3072"
+  "p_nb4096:linalg:-DAB_POTRF_NB=4096"
+  "g_128x64x16s3c2:gemm:"
+  "g_128x64x16s4c2:gemm:-DAB_GEMM_STAGES=4"
+  "g_128x64x32s3c2:gemm:-DAB_GEMM_BK=32"
+  "g_128x128x16s3:gemm:-DAB_GEMM_BN=128 -DAB_GEMM_WARPS_M=2 -DAB_GEMM_WARPS_N=4 -DAB_GEMM_MIN_CTAS=1"
 )
 SKIP_RUN="${SWEEP_SKIP:-}"
 if [ "${1:-build}" = "build" ]; then
@@ -63,7 +61,7 @@ for v in "${VARIANTS[@]}"; do
   if [ "$src" = "linalg" ]; then
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | tee -a $LOG
-    if [ "$tag" = "p_nb1024" ]; then
+    if [ "$tag" = "p_nb2048" ]; then
       AB_POTRF_RECURSIVE=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | sed 's/^/recursive: /' | tee -a $LOG
     fi
   elif [ "$src" = "gemm" ]; then
