@@ -31,7 +31,7 @@ constexpr int TILE = 64;
 //     and the mirror (lane = column, one LDS.128 per row pair) are bank-conflict free;
 //   padded (AB_GRAM_SWIZZLE=0): stage[c * 65 + r], 8-byte accesses (producer 2-way conflicted).
 #ifndef AB_GRAM_SWIZZLE
-#define AB_GRAM_SWIZZLE 1
+#define AB_GRAM_SWIZZLE 0
 #endif
 constexpr bool STAGE_SWIZZLE = AB_GRAM_SWIZZLE != 0;
 constexpr int LDT = STAGE_SWIZZLE ? TILE : TILE + 1;
@@ -43,6 +43,36 @@ constexpr int GRAM_THREADS = 256;
 // ------------------------------------------------------------------------------------------------
 // lean fp64 exp / sqrt
 // ------------------------------------------------------------------------------------------------
+
+// Instruction-count knobs of the fixed-evaluator kernels (the kernel is issue-bound: 82 warp
+// instructions per pair of which 35 FP64, profiles/r01c_*; tools/sweep.sh measures each):
+//   AB_GRAM_ONECHECK  one range check per pass (the exp arguments only; a zero / subnormal /
+//                     non-finite squared distance turns into a NaN argument) with a cold re-evaluation,
+//                     instead of a check-and-patch branch after the sqrt batch and after every exp batch
+//   AB_GRAM_PTRS      loop-carried pointers for the direct / mirror stores and the staging buffer
+//                     instead of 64-bit index arithmetic in every pass
+//   AB_GRAM_EXPMAD    2^n scaling of exp as shift + multiply-add (2 integer instructions, not 3)
+#ifndef AB_GRAM_ONECHECK
+#define AB_GRAM_ONECHECK 0
+#endif
+#ifndef AB_GRAM_PTRS
+#define AB_GRAM_PTRS 0
+#endif
+#ifndef AB_GRAM_EXPMAD
+#define AB_GRAM_EXPMAD 0
+#endif
+
+// res * 2^(m >> SHIFT) for a normal result (no overflow: the argument range is checked)
+template <int SHIFT> __device__ __forceinline__ double exp_scale(double res, int m) {
+#if AB_GRAM_EXPMAD
+  int hi;
+  asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(hi) : "r"(m >> SHIFT), "r"(__double2hiint(res)));
+  return __hiloint2double(hi, __double2loint(res));
+#else
+  return __hiloint2double(__double2hiint(res) + (m & ~((1 << SHIFT) - 1)) * (1 << (20 - SHIFT)),
+                          __double2loint(res));
+#endif
+}
 
 // exp(x) for -708 <= x <= -0 (the argument of every radial kernel): x = (128 n + j) ln2/128 + r,
 // exp(x) = 2^n T[j] (1 + r + ... + r^5/120), |r| <= ln2/256; 10 FP64-pipe instructions, <= 1 ulp.
@@ -64,7 +94,7 @@ __device__ __forceinline__ double exp_core(double x, const double *__restrict__ 
   const double res = fma(tj, q, tj);
   hi_max = max(hi_max, __double2hiint(x));
   // + n * 2^20 on the high word, n = m >> 7 (arithmetic): (m & ~127) * 2^13
-  return __hiloint2double(__double2hiint(res) + (m & ~127) * 8192, __double2loint(res));
+  return exp_scale<7>(res, m);
 }
 
 // Same with the 2048-entry table: |r| <= ln2/4096, degree-3 polynomial, 8 FP64-pipe instructions,
@@ -82,7 +112,7 @@ __device__ __forceinline__ double exp_core_big(double x, const double *__restric
   const double tj = tab[m & 2047];
   const double res = fma(tj, q, tj);
   hi_max = max(hi_max, __double2hiint(x));
-  return __hiloint2double(__double2hiint(res) + (m & ~2047) * 512, __double2loint(res));
+  return exp_scale<11>(res, m);
 }
 
 // Same with a 256-entry table held in shared memory in 16 interleaved copies, copy (lane & 15) at
@@ -106,10 +136,11 @@ __device__ __forceinline__ double exp_core_r256(double x, const double *__restri
   const double tj = tab_lane[(m & 255) * EXP_REPL];
   const double res = fma(tj, q, tj);
   hi_max = max(hi_max, __double2hiint(x));
-  return __hiloint2double(__double2hiint(res) + (m & ~255) * 4096, __double2loint(res));
+  return exp_scale<8>(res, m);
 }
 
 constexpr int EXP_HI_LIMIT = static_cast<int>(0xC0862000u);
+
 
 __device__ __forceinline__ double exp_patch(double x, double fast) {
   // x == +0 or in range: the fast value is right; x < -708: the reference's exp() underflows to a
@@ -136,6 +167,19 @@ __device__ __forceinline__ double sqrt_core(double a, int &hi_min, int &hi_max) 
   return fma(e, h, g);
 }
 
+// the same without range bookkeeping (AB_GRAM_ONECHECK): a zero, subnormal or non-finite argument
+// yields NaN (0 * inf, inf - inf), which the exp range check of the caller catches
+__device__ __forceinline__ double sqrt_core_nocheck(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y;
+  const double h = 0.5 * y;
+  const double r = fma(-h, g, 0.5);
+  g = fma(g, r, g);
+  const double e = fma(-g, g, a);
+  return fma(e, h, g);
+}
+
 __device__ __forceinline__ double sqrt_patch(double a, double fast) {
   if (a >= 2.2250738585072014e-308 && a < INFINITY) {
     return fast;
@@ -156,6 +200,19 @@ constexpr int MODE_SUM = 0, MODE_SUM_NOISE = 1, MODE_SOP = 2, MODE_STACK = 3;
 // exp of NP arguments with one range check for the batch
 // table kinds: plain 128 entries (degree 5) | plain 2048 entries (degree 3) | 256 entries x 16 copies
 constexpr int TAB_128 = 0, TAB_2048 = 1, TAB_R256 = 2;
+
+// exp of NP arguments, no check: hi_acc accumulates the range information for the caller
+template <int NP, int TAB>
+__device__ __forceinline__ void exp_batch_nocheck(const double (&v)[NP],
+                                                  const double *__restrict__ tab, double (&e)[NP],
+                                                  int &hi_acc) {
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    e[i] = TAB == TAB_2048   ? exp_core_big(v[i], tab, hi_acc)
+           : TAB == TAB_R256 ? exp_core_r256(v[i], tab, hi_acc)
+                             : exp_core(v[i], tab, hi_acc);
+  }
+}
 
 template <int NP, int TAB = TAB_128>
 __device__ __forceinline__ void exp_batch(const double (&v)[NP], const double *__restrict__ tab,
@@ -277,6 +334,13 @@ __device__ __noinline__ double eval_stack(const DevProg &P, double d2, double di
 
 template <int MODE> struct EvalProgram {
   static constexpr bool NEED_EQ = MODE != MODE_SUM;
+  static constexpr bool ONE_CHECK = false;
+  template <int NP>
+  __device__ static __forceinline__ bool run_fast(const DevProg &, const double (&)[NP],
+                                                  const double (&)[NP], unsigned, const double *,
+                                                  double (&)[NP]) {
+    return true;
+  }
   static constexpr int TABLE = 128; // doubles of shared memory
   __device__ static __forceinline__ const double *table() { return EXP_TABLE; }
   __device__ static __forceinline__ void fill_table(double *smem, int tid) {
@@ -304,10 +368,11 @@ template <int MODE> struct EvalProgram {
 // Compile-time leaf kinds of EvalFixed.
 enum LeafSig : int { LS_NONE = 0, LS_SE = 1, LS_EXP = 2, LS_M32 = 3, LS_M52 = 4, LS_CONST = 5, LS_NOISE = 6 };
 
-template <int KIND, int NP, int TAB>
+template <int KIND, int NP, int TAB, bool CHECK = true>
 __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP],
                                            const double (&dist)[NP], unsigned eqmask,
-                                           const double *__restrict__ tab, double (&out)[NP]) {
+                                           const double *__restrict__ tab, double (&out)[NP],
+                                           int &hi_acc) {
   if constexpr (KIND == LS_NONE) {
     return;
   } else if constexpr (KIND == LS_CONST) {
@@ -337,7 +402,11 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
         v[i] = a1 * dist[i];
       }
     }
-    exp_batch<NP, TAB>(v, tab, e);
+    if constexpr (CHECK) {
+      exp_batch<NP, TAB>(v, tab, e);
+    } else {
+      exp_batch_nocheck<NP, TAB>(v, tab, e, hi_acc);
+    }
     if constexpr (KIND == LS_M32) {
       const double b1 = o.b1;
 #pragma unroll
@@ -365,7 +434,7 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
 // reads a plain table through L1 instead of shared memory (measured slower: L1/shared is the
 // kernel's busiest unit).
 #ifndef AB_GRAM_TABLE
-#define AB_GRAM_TABLE 2
+#define AB_GRAM_TABLE 1
 #endif
 constexpr int FIXED_TABLE = AB_GRAM_TABLE;
 #ifdef AB_GRAM_TABLE_GLOBAL
@@ -401,9 +470,30 @@ template <int K0, int K1, int K2, int TAB = FIXED_TABLE> struct EvalFixed {
     for (int i = 0; i < NP; ++i) {
       out[i] = 0.;
     }
-    fixed_term<K0, NP, TAB>(P.ops[0], d2, dist, eqmask, tab, out);
-    fixed_term<K1, NP, TAB>(P.ops[1], d2, dist, eqmask, tab, out);
-    fixed_term<K2, NP, TAB>(P.ops[2], d2, dist, eqmask, tab, out);
+    int unused = 0;
+    fixed_term<K0, NP, TAB>(P.ops[0], d2, dist, eqmask, tab, out, unused);
+    fixed_term<K1, NP, TAB>(P.ops[1], d2, dist, eqmask, tab, out, unused);
+    fixed_term<K2, NP, TAB>(P.ops[2], d2, dist, eqmask, tab, out, unused);
+  }
+  // The same arithmetic without any branch; returns true when some exp argument was out of range
+  // (then `out` is garbage and the caller re-evaluates the pass through run()).  Because every use
+  // of `dist` is an exp argument a * dist with a finite a, a NaN distance (the branch-free sqrt of a
+  // zero, subnormal or non-finite squared distance) is caught by the same test.
+  static constexpr bool ONE_CHECK = AB_GRAM_ONECHECK != 0;
+  template <int NP>
+  __device__ static __forceinline__ bool run_fast(const DevProg &P, const double (&d2)[NP],
+                                                  const double (&dist)[NP], unsigned eqmask,
+                                                  const double *__restrict__ tab,
+                                                  double (&out)[NP]) {
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      out[i] = 0.;
+    }
+    int hi_acc = EXP_HI_LIMIT;
+    fixed_term<K0, NP, TAB, false>(P.ops[0], d2, dist, eqmask, tab, out, hi_acc);
+    fixed_term<K1, NP, TAB, false>(P.ops[1], d2, dist, eqmask, tab, out, hi_acc);
+    fixed_term<K2, NP, TAB, false>(P.ops[2], d2, dist, eqmask, tab, out, hi_acc);
+    return hi_acc > EXP_HI_LIMIT;
   }
 };
 
@@ -568,6 +658,20 @@ __device__ __forceinline__ void mirror_slice(const double *__restrict__ stage,
   }
 }
 
+// The same slice of an interior tile through loop-carried pointers (AB_GRAM_PTRS, padded layout):
+// dst = &out[j0 + lane, i0 + rbase], src = &stage[lane][rbase].
+template <int PARTS>
+__device__ __forceinline__ void mirror_slice_ptr(double *__restrict__ dst,
+                                                 const double *__restrict__ src, int64_t ld) {
+  constexpr int KS = 8 / PARTS;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    gram_store(dst, src[k]);
+    gram_store(dst + 32, src[32 * LDT + k]);
+    dst += ld;
+  }
+}
+
 // Persistent CTAs: each CTA walks the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
 //   * the features of the next tile are fetched into registers while the current one is evaluated
 //     (global-load latency, table load and the store drain at exit are paid once per CTA);
@@ -610,6 +714,10 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   // pending mirror of the previous tile: bit 0 = pending, bit 1 = interior, bit 2 = staging buffer
   unsigned pend = 0, pI = 0, pJ = 0;
   unsigned buf = 0;
+  constexpr bool USE_PTRS = AB_GRAM_PTRS != 0;
+  static_assert(!(USE_PTRS && STAGE_SWIZZLE), "AB_GRAM_PTRS is written for the padded staging layout");
+  double *mptr = out;             // next slice of the pending mirror (interior tiles, AB_GRAM_PTRS)
+  const double *msrc = stage0;
 
   while (t < ntiles) {
     const unsigned cI = I, cJ = J;
@@ -648,6 +756,10 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
       }
     }
     const int64_t gi = i0 + r0;
+    // AB_GRAM_PTRS: loop-carried pointers (pass p handles columns p * 8 COLS + warp * COLS + k)
+    double *dptr = out + gi + (j0 + warp * COLS) * ld; // direct store, column k = 0
+    const double *yp = ys + warp * COLS * DIM;         // y features of column k = 0
+    double *sp = stage + warp * COLS * LDT + r0;       // staging element (column k = 0, row r0)
 
 #pragma unroll 1
     for (int pass = 0; pass < PASSES; ++pass) {
@@ -660,7 +772,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
         double yj[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
-          yj[d] = ys[c * DIM + d];
+          yj[d] = USE_PTRS ? yp[k * DIM + d] : ys[c * DIM + d];
         }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -682,26 +794,45 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
           }
         }
       }
-      if (need_dist) {
-        int hi_min = 0x00100000, hi_max = 0x7fefffff;
-#pragma unroll
-        for (int i = 0; i < NPAIR; ++i) {
-          dist[i] = sqrt_core(d2[i], hi_min, hi_max);
-        }
-        if (hi_min < 0x00100000 || hi_max > 0x7fefffff) {
-          // rare: a zero / subnormal / non-finite squared distance (e.g. the diagonal)
+      if constexpr (EV::ONE_CHECK) {
+        if (need_dist) {
 #pragma unroll
           for (int i = 0; i < NPAIR; ++i) {
-            dist[i] = sqrt_patch(d2[i], dist[i]);
+            dist[i] = sqrt_core_nocheck(d2[i]);
           }
         }
+        if (EV::template run_fast<NPAIR>(P, d2, dist, eqmask, tab, vals)) {
+          // rare (the diagonal, coincident points, underflowing or non-finite arguments): repair the
+          // distances lane by lane and take the checked evaluator; in-range lanes get the same bits
+          if (need_dist) {
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) {
+              dist[i] = sqrt_patch(d2[i], dist[i]);
+            }
+          }
+          EV::template run<NPAIR>(P, d2, dist, eqmask, tab, vals);
+        }
+      } else {
+        if (need_dist) {
+          int hi_min = 0x00100000, hi_max = 0x7fefffff;
+#pragma unroll
+          for (int i = 0; i < NPAIR; ++i) {
+            dist[i] = sqrt_core(d2[i], hi_min, hi_max);
+          }
+          if (hi_min < 0x00100000 || hi_max > 0x7fefffff) {
+            // rare: a zero / subnormal / non-finite squared distance (e.g. the diagonal)
+#pragma unroll
+            for (int i = 0; i < NPAIR; ++i) {
+              dist[i] = sqrt_patch(d2[i], dist[i]);
+            }
+          }
+        }
+        EV::template run<NPAIR>(P, d2, dist, eqmask, tab, vals);
       }
-
-      EV::template run<NPAIR>(P, d2, dist, eqmask, tab, vals);
 
       // direct tile: rows i0 + r0 (+1), columns j0 + c; 16-byte stores, 512 contiguous bytes/warp
       if (interior) {
-        double *dst = out + gi + (j0 + cbase) * ld;
+        double *dst = USE_PTRS ? dptr : out + gi + (j0 + cbase) * ld;
 #pragma unroll
         for (int k = 0; k < COLS; ++k) {
           gram_store(reinterpret_cast<double2 *>(dst), make_double2(vals[2 * k], vals[2 * k + 1]));
@@ -732,6 +863,9 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
           if (STAGE_SWIZZLE) {
             *reinterpret_cast<double2 *>(stage + stage_granule(c, lane)) =
                 make_double2(vals[2 * k], vals[2 * k + 1]);
+          } else if (USE_PTRS) {
+            sp[k * LDT] = vals[2 * k];
+            sp[k * LDT + 1] = vals[2 * k + 1];
           } else {
             stage[c * LDT + r0] = vals[2 * k];
             stage[c * LDT + r0 + 1] = vals[2 * k + 1];
@@ -739,8 +873,19 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
         }
       }
       if (SYM && (pend & 1u)) {
-        mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
-                             pass, lane, warp);
+        if (USE_PTRS && (pend & 2u)) {
+          mirror_slice_ptr<PASSES>(mptr, msrc, ld);
+          mptr += (8 / PASSES) * ld;
+          msrc += 8 / PASSES;
+        } else {
+          mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
+                               pass, lane, warp);
+        }
+      }
+      if (USE_PTRS) {
+        dptr += static_cast<int64_t>(8 * COLS) * ld;
+        yp += 8 * COLS * DIM;
+        sp += 8 * COLS * LDT;
       }
     }
 
@@ -748,6 +893,10 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
       pend = mirror ? (1u | (interior ? 2u : 0u) | (buf << 2)) : 0u;
       pI = cI;
       pJ = cJ;
+      if (USE_PTRS) { // slice 0 of the pending mirror: rows j0 + lane (+32), columns i0 + warp * 8 ...
+        mptr = out + (j0 + lane) + (i0 + warp * 8) * ld;
+        msrc = stage + lane * LDT + warp * 8;
+      }
       if (mirror) {
         buf ^= 1u;
       }
@@ -758,8 +907,14 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
     __syncthreads();
 #pragma unroll 1
     for (int part = 0; part < PASSES; ++part) {
-      mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u, part,
-                           lane, warp);
+      if (USE_PTRS && (pend & 2u)) {
+        mirror_slice_ptr<PASSES>(mptr, msrc, ld);
+        mptr += (8 / PASSES) * ld;
+        msrc += 8 / PASSES;
+      } else {
+        mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
+                             part, lane, warp);
+      }
     }
   }
 }

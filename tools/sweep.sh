@@ -10,19 +10,18 @@ NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c+
 OUT=tools/sweep
 # tag : source : defines
 VARIANTS=(
-  "k_new:gram_fixed:"
-  "k_old:gram_fixed:-DAB_GRAM_TABLE=1 -DAB_GRAM_SWIZZLE=0"
-  "k_r256_pad:gram_fixed:-DAB_GRAM_TABLE=2 -DAB_GRAM_SWIZZLE=0"
+  "k_base:gram_fixed:"
+  "k_all3:gram_fixed:-DAB_GRAM_PTRS=1 -DAB_GRAM_ONECHECK=1 -DAB_GRAM_EXPMAD=1"
+  "k_ptrs:gram_fixed:-DAB_GRAM_PTRS=1"
+  "k_onecheck:gram_fixed:-DAB_GRAM_ONECHECK=1"
+  "k_expmad:gram_fixed:-DAB_GRAM_EXPMAD=1"
+  "k_check_mad:gram_fixed:-DAB_GRAM_ONECHECK=1 -DAB_GRAM_EXPMAD=1"
+  "k_r256_swz:gram_fixed:-DAB_GRAM_TABLE=2 -DAB_GRAM_SWIZZLE=1"
   "k_t2048_swz:gram_fixed:-DAB_GRAM_TABLE=1 -DAB_GRAM_SWIZZLE=1"
-  "k_new_cols4:gram_fixed:-DAB_GRAM_COLS=4"
-  "k_new_cs:gram_fixed:-DAB_GRAM_STREAM_STORES=1"
   "p_nb2048:linalg:"
   "p_nb1024:linalg:-DAB_POTRF_NB=1024"
-  "p_nb3072:linalg:-DAB_POTRF_NB=3072"
   "p_nb4096:linalg:-DAB_POTRF_NB=4096"
   "g_128x64x16s3c2:gemm:"
-  "g_128x64x16s4c2:gemm:-DAB_GEMM_STAGES=4"
-  "g_128x64x32s3c2:gemm:-DAB_GEMM_BK=32"
   "g_128x128x16s3:gemm:-DAB_GEMM_BN=128 -DAB_GEMM_WARPS_M=2 -DAB_GEMM_WARPS_N=4 -DAB_GEMM_MIN_CTAS=1"
 )
 SKIP_RUN="${SWEEP_SKIP:-}"
@@ -31,6 +30,7 @@ if [ "${1:-build}" = "build" ]; then
   mkdir -p $OUT
   for v in "${VARIANTS[@]}"; do
     IFS=: read -r tag src defs <<< "$v"
+    if [ -n "${SWEEP_ONLY:-}" ]; then case "$tag" in ${SWEEP_ONLY}) ;; *) continue;; esac; fi
     (
       objs=$(ls $CS/build/*.o)
       mine=""
@@ -68,6 +68,9 @@ for v in "${VARIANTS[@]}"; do
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gemm_bench.py 8 2>&1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
   else
+    if [ -n "${SWEEP_TEST:-}" ]; then
+      ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 200 python -m pytest $SWEEP_TEST -m gpu -q -x 2>&1 | tail -3 | tee -a $LOG
+    fi
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gram_bench.py 32768 7 3 6 2>&1 | tail -1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gram_bench.py 32768 7 3 6 1 2>&1 | tail -1 | tee -a $LOG
   fi
