@@ -53,13 +53,13 @@ constexpr int GRAM_THREADS = 256;
 //                     instead of 64-bit index arithmetic in every pass
 //   AB_GRAM_EXPMAD    2^n scaling of exp as shift + multiply-add (2 integer instructions, not 3)
 #ifndef AB_GRAM_ONECHECK
-#define AB_GRAM_ONECHECK 0
+#define AB_GRAM_ONECHECK 1
 #endif
 #ifndef AB_GRAM_PTRS
 #define AB_GRAM_PTRS 0
 #endif
 #ifndef AB_GRAM_EXPMAD
-#define AB_GRAM_EXPMAD 0
+#define AB_GRAM_EXPMAD 1
 #endif
 
 // res * 2^(m >> SHIFT) for a normal result (no overflow: the argument range is checked)
