@@ -279,7 +279,9 @@ def run_device(args):
                                "(MEASURED_PEAKS.json carries no fp64 figure)",
                 "traffic": None,
                 "note": "achieved = 2*N^3/3 algorithmic flops / CUDA-event time of the two "
-                        "factorisation phases (panel kernels included)"}
+                        "factorisation phases (panel kernels included); tensor-bound kernel: ncu of the "
+                        "isolated 8192^3 launch reads 35.2 GB + writes 0.54 GB = 12 % of DRAM peak "
+                        "(profiles/r01cdef_ncu_and_probe_summary.md)"}
 
     # ---- Gram roofline at configs[1] -----------------------------------------------------------
     gram_line = None
@@ -303,7 +305,12 @@ def run_device(args):
         gram_line = {"bound": "hbm", "kernel": "ab::gram_kernel<3,sym> SE+Matern52 full symmetric",
                      "n": ng, "achieved": gbytes / (best * 1e-3), "peak": hbm, "unit": "GB/s",
                      "frac": gbytes / (best * 1e-3) / hbm, "peak_source": peak_src,
-                     "ms": best, "traffic": None}
+                     "ms": best,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch at n = 32768 from the
+                     # ncu --set full capture of round 1 (profiles/r01cdef_ncu_and_probe_summary.md):
+                     # 8.533 GB written + 0.062 GB read = the algorithmic 8.590 GB (no re-reads)
+                     "traffic": (8.594532e9 if ng == 32768 else None),
+                     "traffic_source": "ncu r01c" if ng == 32768 else None}
         del flush
         fg.free()
         h.trim()
