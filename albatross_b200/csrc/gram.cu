@@ -21,7 +21,7 @@ namespace ab {
 // host: postfix program -> device program
 // ------------------------------------------------------------------------------------------------
 
-static bool leaf_to_dev(const ab_op &o, DevOp *d) {
+static bool leaf_to_dev_raw(const ab_op &o, DevOp *d) {
   d->flags = 0;
   d->a2 = d->a1 = d->b2 = d->b1 = 0.;
   const double l = o.p0;
@@ -63,6 +63,16 @@ static bool leaf_to_dev(const ab_op &o, DevOp *d) {
   default:
     return false;
   }
+}
+
+static bool leaf_to_dev(const ab_op &o, DevOp *d) {
+  d->ab1 = d->ab2 = 0.;
+  if (!leaf_to_dev_raw(o, d)) {
+    return false;
+  }
+  d->ab1 = d->amp * d->b1;
+  d->ab2 = d->amp * d->b2;
+  return true;
 }
 
 int compile_program(const ab_op *prog, int nops, DevProg *out) {

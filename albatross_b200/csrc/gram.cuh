@@ -34,6 +34,7 @@ struct DevOp {
   int kind;
   int flags;
   double a2, a1, b2, b1, amp;
+  double ab1, ab2; // amp * b1, amp * b2 (AB_GRAM_AMPFOLD: amplitude folded into the polynomial)
 };
 
 // mode 0: "sum of products" — expr := term (+ term)*, term := leaf (* leaf)*, evaluated left to

@@ -61,6 +61,22 @@ constexpr int GRAM_THREADS = 256;
 #ifndef AB_GRAM_EXPMAD
 #define AB_GRAM_EXPMAD 1
 #endif
+// Round-2 candidates (compile-checked only so far; tools/sweep.sh k_r2_*), all aimed at the cost table
+// of tools/issue_probe.cu — a DFMA with three distinct register sources costs 3 cycles instead of 2,
+// IMAD / LOP3 / SHF cost 1-2 each next to FP64 work:
+//   AB_GRAM_QFORM    expm1(r) as r * fma(r, p, 1) (two 2-source instructions) instead of fma(p, r*r, r)
+//   AB_GRAM_AMPFOLD  amplitude folded into the Matern polynomial coefficients (one FP64 less per term)
+//   AB_GRAM_OFF32    interior-tile store addresses as 64-bit tile base + 32-bit element offset
+//                    (one IMAD.WIDE per address) instead of 64-bit index arithmetic in every pass
+#ifndef AB_GRAM_QFORM
+#define AB_GRAM_QFORM 0
+#endif
+#ifndef AB_GRAM_AMPFOLD
+#define AB_GRAM_AMPFOLD 0
+#endif
+#ifndef AB_GRAM_OFF32
+#define AB_GRAM_OFF32 0
+#endif
 
 // res * 2^(m >> SHIFT) for a normal result (no overflow: the argument range is checked)
 template <int SHIFT> __device__ __forceinline__ double exp_scale(double res, int m) {
@@ -107,8 +123,12 @@ __device__ __forceinline__ double exp_core_big(double x, const double *__restric
   double r = fma(mf, -0x1.62e42fef00000p-12, x);
   r = fma(mf, -0x1.473de6af278edp-45, r);
   const double p = fma(r, 0.16666666666666666, 0.5);
+#if AB_GRAM_QFORM
+  const double q = r * fma(r, p, 1.); // expm1(r)
+#else
   const double r2 = r * r;
   const double q = fma(p, r2, r); // expm1(r)
+#endif
   const double tj = tab[m & 2047];
   const double res = fma(tj, q, tj);
   hi_max = max(hi_max, __double2hiint(x));
@@ -407,6 +427,22 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
     } else {
       exp_batch_nocheck<NP, TAB>(v, tab, e, hi_acc);
     }
+    const double amp = o.amp;
+#if AB_GRAM_AMPFOLD
+    if constexpr (KIND == LS_M32 || KIND == LS_M52) {
+      // amp * (1 + b1 d [+ b2 d^2]) * e as fma(poly', e, out), poly' = amp + (amp b1) d [+ (amp b2) d^2]
+      const double ab1 = o.ab1, ab2 = o.ab2;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        double poly = fma(ab1, dist[i], amp);
+        if constexpr (KIND == LS_M52) {
+          poly = fma(ab2, d2[i], poly);
+        }
+        out[i] = fma(poly, e[i], out[i]);
+      }
+      return;
+    }
+#endif
     if constexpr (KIND == LS_M32) {
       const double b1 = o.b1;
 #pragma unroll
@@ -420,7 +456,6 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
         e[i] = e[i] * fma(b2, d2[i], fma(b1, dist[i], 1.));
       }
     }
-    const double amp = o.amp;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
       out[i] = fma(amp, e[i], out[i]);
@@ -672,6 +707,35 @@ __device__ __forceinline__ void mirror_slice_ptr(double *__restrict__ dst,
   }
 }
 
+// Hides the provenance of a pointer from the optimiser.
+__device__ __forceinline__ double *opaque_ptr(double *p) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  asm volatile("" : "+l"(v));
+  double *q = reinterpret_cast<double *>(v);
+  __builtin_assume(__isGlobal(q)); // keep st.global (a pointer of unknown provenance stores generically)
+  return q;
+}
+
+// The same slice of an interior tile addressed as tile base + 32-bit element offset (AB_GRAM_OFF32,
+// padded layout): mbase = &out[j0, i0]; one IMAD.WIDE per address instead of 64-bit index arithmetic.
+template <int PARTS>
+__device__ __forceinline__ void mirror_slice_off(const double *__restrict__ stage,
+                                                 double *__restrict__ mbase, unsigned ld32, int part,
+                                                 int lane, int warp) {
+  constexpr int KS = 8 / PARTS;
+  __builtin_assume(__isGlobal(mbase));
+  const int rbase = warp * 8 + part * KS;
+  const double *src = stage + lane * LDT + rbase;
+  unsigned off = static_cast<unsigned>(lane) + static_cast<unsigned>(rbase) * ld32;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    double *dst = mbase + off;
+    gram_store(dst, src[k]);
+    gram_store(dst + 32, src[32 * LDT + k]);
+    off += ld32;
+  }
+}
+
 // Persistent CTAs: each CTA walks the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
 //   * the features of the next tile are fetched into registers while the current one is evaluated
 //     (global-load latency, table load and the store drain at exit are paid once per CTA);
@@ -714,6 +778,11 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   // pending mirror of the previous tile: bit 0 = pending, bit 1 = interior, bit 2 = staging buffer
   unsigned pend = 0, pI = 0, pJ = 0;
   unsigned buf = 0;
+  constexpr bool USE_OFF32 = AB_GRAM_OFF32 != 0;
+  static_assert(!(USE_OFF32 && STAGE_SWIZZLE), "AB_GRAM_OFF32 is written for the padded staging layout");
+  static_assert(!(USE_OFF32 && AB_GRAM_PTRS != 0), "AB_GRAM_OFF32 and AB_GRAM_PTRS are alternatives");
+  const unsigned ld32 = static_cast<unsigned>(ld);
+  double *mbase = out; // &out[j0, i0] of the pending mirror (AB_GRAM_OFF32)
   constexpr bool USE_PTRS = AB_GRAM_PTRS != 0;
   static_assert(!(USE_PTRS && STAGE_SWIZZLE), "AB_GRAM_PTRS is written for the padded staging layout");
   double *mptr = out;             // next slice of the pending mirror (interior tiles, AB_GRAM_PTRS)
@@ -725,7 +794,8 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
     const int64_t j0 = static_cast<int64_t>(cJ) * TILE;
     const bool mirror = SYM && cI != cJ && !(flags & AB_GRAM_LOWER_ONLY);
     // interior tile of a 16-byte aligned output: no bounds checks anywhere below
-    const bool interior = (i0 + TILE <= n) && (j0 + TILE <= m) && !(flags & GRAM_UNALIGNED);
+    const bool interior = (i0 + TILE <= n) && (j0 + TILE <= m) && !(flags & GRAM_UNALIGNED) &&
+                          (!USE_OFF32 || (ld >> 24) == 0); // 64 * ld elements fit a 32-bit offset
     double *stage = stage0 + buf * STAGE;
 
     // every reader of xs / ys of the previous tile is done, every slice of the mirror before the
@@ -756,6 +826,10 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
       }
     }
     const int64_t gi = i0 + r0;
+    double *tbase = out + i0 + j0 * ld; // AB_GRAM_OFF32: &out[i0, j0]
+    if (USE_OFF32) {
+      tbase = opaque_ptr(tbase); // keep base + 32-bit offset (else ptxas re-derives 64-bit indices)
+    }
     // AB_GRAM_PTRS: loop-carried pointers (pass p handles columns p * 8 COLS + warp * COLS + k)
     double *dptr = out + gi + (j0 + warp * COLS) * ld; // direct store, column k = 0
     const double *yp = ys + warp * COLS * DIM;         // y features of column k = 0
@@ -832,11 +906,21 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
 
       // direct tile: rows i0 + r0 (+1), columns j0 + c; 16-byte stores, 512 contiguous bytes/warp
       if (interior) {
-        double *dst = USE_PTRS ? dptr : out + gi + (j0 + cbase) * ld;
+        if (USE_OFF32) {
+          unsigned off = static_cast<unsigned>(r0) + static_cast<unsigned>(cbase) * ld32;
 #pragma unroll
-        for (int k = 0; k < COLS; ++k) {
-          gram_store(reinterpret_cast<double2 *>(dst), make_double2(vals[2 * k], vals[2 * k + 1]));
-          dst += ld;
+          for (int k = 0; k < COLS; ++k) {
+            gram_store(reinterpret_cast<double2 *>(tbase + off),
+                       make_double2(vals[2 * k], vals[2 * k + 1]));
+            off += ld32;
+          }
+        } else {
+          double *dst = USE_PTRS ? dptr : out + gi + (j0 + cbase) * ld;
+#pragma unroll
+          for (int k = 0; k < COLS; ++k) {
+            gram_store(reinterpret_cast<double2 *>(dst), make_double2(vals[2 * k], vals[2 * k + 1]));
+            dst += ld;
+          }
         }
       } else {
         const bool unaligned = flags & GRAM_UNALIGNED;
@@ -877,6 +961,8 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
           mirror_slice_ptr<PASSES>(mptr, msrc, ld);
           mptr += (8 / PASSES) * ld;
           msrc += 8 / PASSES;
+        } else if (USE_OFF32 && (pend & 2u)) {
+          mirror_slice_off<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, mbase, ld32, pass, lane, warp);
         } else {
           mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
                                pass, lane, warp);
@@ -893,6 +979,9 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
       pend = mirror ? (1u | (interior ? 2u : 0u) | (buf << 2)) : 0u;
       pI = cI;
       pJ = cJ;
+      if (USE_OFF32) {
+        mbase = opaque_ptr(out + j0 + i0 * ld);
+      }
       if (USE_PTRS) { // slice 0 of the pending mirror: rows j0 + lane (+32), columns i0 + warp * 8 ...
         mptr = out + (j0 + lane) + (i0 + warp * 8) * ld;
         msrc = stage + lane * LDT + warp * 8;
@@ -911,6 +1000,8 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
         mirror_slice_ptr<PASSES>(mptr, msrc, ld);
         mptr += (8 / PASSES) * ld;
         msrc += 8 / PASSES;
+      } else if (USE_OFF32 && (pend & 2u)) {
+        mirror_slice_off<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, mbase, ld32, part, lane, warp);
       } else {
         mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
                              part, lane, warp);

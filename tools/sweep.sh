@@ -11,13 +11,12 @@ OUT=tools/sweep
 # tag : source : defines
 VARIANTS=(
   "k_base:gram_fixed:"
-  "k_all3:gram_fixed:-DAB_GRAM_PTRS=1 -DAB_GRAM_ONECHECK=1 -DAB_GRAM_EXPMAD=1"
-  "k_ptrs:gram_fixed:-DAB_GRAM_PTRS=1"
-  "k_onecheck:gram_fixed:-DAB_GRAM_ONECHECK=1"
-  "k_expmad:gram_fixed:-DAB_GRAM_EXPMAD=1"
-  "k_check_mad:gram_fixed:-DAB_GRAM_ONECHECK=1 -DAB_GRAM_EXPMAD=1"
-  "k_r256_swz:gram_fixed:-DAB_GRAM_TABLE=2 -DAB_GRAM_SWIZZLE=1"
-  "k_t2048_swz:gram_fixed:-DAB_GRAM_TABLE=1 -DAB_GRAM_SWIZZLE=1"
+  "k_r2_off32:gram_fixed:-DAB_GRAM_OFF32=1"
+  "k_r2_qform:gram_fixed:-DAB_GRAM_QFORM=1"
+  "k_r2_ampfold:gram_fixed:-DAB_GRAM_AMPFOLD=1"
+  "k_r2_all:gram_fixed:-DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1"
+  "k_r2_all_cols4:gram_fixed:-DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_COLS=4"
+  "k_r1_nocheck:gram_fixed:-DAB_GRAM_ONECHECK=0 -DAB_GRAM_EXPMAD=0"
   "p_nb2048:linalg:"
   "p_nb1024:linalg:-DAB_POTRF_NB=1024"
   "p_nb4096:linalg:-DAB_POTRF_NB=4096"
