@@ -135,6 +135,62 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t
   }
 }
 
+// AB_GEMM_FASTLOAD (round-2 candidate, compile-checked only so far; tools/sweep.sh g_fast*): the k-loop
+// above spends 310 non-DMMA instructions per 64 DMMA, almost all of them the 64-bit address and
+// predicate arithmetic load_tile redoes for every k-tile (profiles/r01cdef_ncu_and_probe_summary.md).
+// For CTA tiles that lie fully inside the operands (16-byte aligned, k a multiple of BK) everything but
+// the k offset is loop invariant: a thread keeps one source pointer and one shared-memory offset per
+// operand; chunk `it` of a k-tile is a fixed stride away from chunk 0 in both address spaces.
+#ifndef AB_GEMM_FASTLOAD
+#define AB_GEMM_FASTLOAD 0
+#endif
+
+template <int EXT, bool KMAJOR> struct FastTile {
+  static constexpr int ITERS = (BK * EXT / 2) / GEMM_THREADS;
+  // chunk = tid + it * GEMM_THREADS
+  //   !KMAJOR: kk = chunk / (EXT / 2), ic = 2 (chunk % (EXT / 2)); GEMM_THREADS % (EXT / 2) == 0, so ic is
+  //            the same for every it and kk advances by KSTEP = GEMM_THREADS / (EXT / 2)
+  //    KMAJOR: i = chunk / (BK / 2), kc = 2 (chunk % (BK / 2)); i advances by ISTEP = GEMM_THREADS / (BK / 2)
+  static constexpr int KSTEP = GEMM_THREADS / (EXT / 2);
+  static constexpr int ISTEP = GEMM_THREADS / (BK / 2);
+  static_assert(KMAJOR || GEMM_THREADS % (EXT / 2) == 0, "loader shape (fast path)");
+  static_assert(!KMAJOR || GEMM_THREADS % (BK / 2) == 0, "loader shape (fast path)");
+  static constexpr int S_IT = KMAJOR ? ISTEP * LDK : KSTEP * (EXT + 4); // smem elements between chunks
+
+  const double *g0; // chunk 0 of k-tile 0
+  int64_t g_it;     // global elements between chunks of one k-tile
+  int64_t g_kt;     // global elements between k-tiles
+  int s0;           // smem element offset of chunk 0 inside a stage
+
+  __device__ __forceinline__ FastTile(const double *g, int64_t ld, int64_t i0, int tid) {
+    if (!KMAJOR) {
+      const int kk = tid / (EXT / 2);
+      const int ic = (tid % (EXT / 2)) * 2;
+      g0 = g + (i0 + ic) + static_cast<int64_t>(kk) * ld;
+      g_it = static_cast<int64_t>(KSTEP) * ld;
+      g_kt = static_cast<int64_t>(BK) * ld;
+      s0 = kk * (EXT + 4) + ic;
+    } else {
+      const int i = tid / (BK / 2);
+      const int kc = (tid % (BK / 2)) * 2;
+      g0 = g + kc + (i0 + i) * ld;
+      g_it = static_cast<int64_t>(ISTEP) * ld;
+      g_kt = BK;
+      s0 = i * LDK + kc;
+    }
+  }
+  // all chunks of k-tile kt into the stage at `stage`
+  __device__ __forceinline__ void issue(double *stage, int kt) const {
+    const double *src = g0 + static_cast<int64_t>(kt) * g_kt;
+    double *dst = stage + s0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      cp_async16(dst + it * S_IT, src, 16);
+      src += g_it;
+    }
+  }
+};
+
 template <int EXT, bool KMAJOR>
 __device__ __forceinline__ double frag(const double *smem, int idx, int kk) {
   return KMAJOR ? smem[idx * LDK + kk] : smem[kk * (EXT + 4) + idx];
@@ -198,13 +254,23 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
   }
 
   const int ktiles = static_cast<int>((k + BK - 1) / BK);
+  // fast loader: this CTA's tile lies fully inside both operands, 16-byte aligned, no k remainder
+  const bool fast = AB_GEMM_FASTLOAD && a_vec && b_vec && (m0 + BM <= m) && (n0 + BN <= n) &&
+                    (k % BK == 0);
+  const FastTile<BM, A_KMAJOR> fa_tile(A, lda, m0, tid);
+  const FastTile<BN, B_KMAJOR> fb_tile(B, ldb, n0, tid);
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) {
-      load_tile<BM, A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(s) * BK, k, tid,
-                          a_vec);
-      load_tile<BN, B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(s) * BK, k, tid,
-                          b_vec);
+      if (fast) {
+        fa_tile.issue(sA + s * A_ELEMS, s);
+        fb_tile.issue(sB + s * B_ELEMS, s);
+      } else {
+        load_tile<BM, A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(s) * BK, k, tid,
+                                a_vec);
+        load_tile<BN, B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(s) * BK, k, tid,
+                                b_vec);
+      }
     }
     cp_async_commit();
   }
@@ -216,10 +282,15 @@ gemm_kernel(int64_t m, int64_t n, int64_t k, double alpha, const double *A, int6
       const int nt = kt + STAGES - 1;
       if (nt < ktiles) {
         const int s = nt % STAGES;
-        load_tile<BM, A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(nt) * BK, k, tid,
-                            a_vec);
-        load_tile<BN, B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(nt) * BK, k, tid,
-                            b_vec);
+        if (fast) {
+          fa_tile.issue(sA + s * A_ELEMS, nt);
+          fb_tile.issue(sB + s * B_ELEMS, nt);
+        } else {
+          load_tile<BM, A_KMAJOR>(sA + s * A_ELEMS, A, lda, m0, m, static_cast<int64_t>(nt) * BK, k,
+                                  tid, a_vec);
+          load_tile<BN, B_KMAJOR>(sB + s * B_ELEMS, B, ldb, n0, n, static_cast<int64_t>(nt) * BK, k,
+                                  tid, b_vec);
+        }
       }
       cp_async_commit();
     }

@@ -21,6 +21,8 @@ VARIANTS=(
   "p_nb1024:linalg:-DAB_POTRF_NB=1024"
   "p_nb4096:linalg:-DAB_POTRF_NB=4096"
   "g_128x64x16s3c2:gemm:"
+  "g_fast:gemm:-DAB_GEMM_FASTLOAD=1"
+  "g_fast_s4:gemm:-DAB_GEMM_FASTLOAD=1 -DAB_GEMM_STAGES=4"
   "g_128x128x16s3:gemm:-DAB_GEMM_BN=128 -DAB_GEMM_WARPS_M=2 -DAB_GEMM_WARPS_N=4 -DAB_GEMM_MIN_CTAS=1"
 )
 SKIP_RUN="${SWEEP_SKIP:-}"
