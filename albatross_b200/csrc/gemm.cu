@@ -496,6 +496,12 @@ int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double
     AB_LAUNCHED(h);
     return AB_OK;
   }
+  if (tb && !ta && gemm_tma_enabled()) {
+    const int s = gemm_nt_tma(h, lower, m, n, k, alpha, A, B, beta, C);
+    if (s != AB_ERR_UNSUPPORTED) {
+      return s;
+    }
+  }
   if (ta && tb) {
     return launch<true, true>(h, lower, m, n, k, alpha, A, B, beta, C);
   } else if (ta) {

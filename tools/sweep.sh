@@ -67,6 +67,13 @@ for v in "${VARIANTS[@]}"; do
       AB_POTRF_RECURSIVE=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | sed 's/^/recursive: /' | tee -a $LOG
     fi
   elif [ "$src" = "gemm" ]; then
+    if [ "$tag" = "g_128x64x16s3c2" ]; then
+      # the TMA + mbarrier variant of the NT product (gemm_tma.cu) is a run-time switch of the same build;
+      # first parity (under a short timeout: a pipeline bug would hang), then timing
+      AB_GEMM_TMA=1 timeout 120 python -m pytest tests/test_gpu_gemm.py -m gpu -q -x 2>&1 | tail -3 | sed 's/^/tma: /' | tee -a $LOG
+      AB_GEMM_TMA=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 120 python tools/gemm_bench.py 8 2>&1 | sed 's/^/tma: /' | tee -a $LOG
+      AB_GEMM_TMA=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 120 python tools/potrf_bench.py 32768 2>&1 | sed 's/^/tma: /' | tee -a $LOG
+    fi
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gemm_bench.py 8 2>&1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
   else
