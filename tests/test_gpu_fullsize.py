@@ -6,7 +6,13 @@ them: the reference's LDLT needs 6.4 h and 96 GiB at N = 65 536).  Everything go
   configs[2]  exact GP, N = 65 536, 3-D, SE + IndependentNoise: K alpha = y, the NLL assembled from its
               pieces, and the value the 1-GPU recursion and the 2-GPU block-cyclic factorisation agreed on
               to 3e-13 (profiles/r01_bench_n65536.json, profiles/r01_bench_2gpu_n65536.json).
+  configs[3]  LOO / leave-one-group-out CV, N = 32 768 (bench_loo_cv shape): the closed forms of
+              evaluation/cross_validation_utils.hpp:132-286 checked through independent solves.  Written
+              when the round-1 GPU budget was already spent: runs only with AB_RUN_UNVERIFIED=1 until its
+              first green run on a B200 (tools/gpu_r2_visit1.sh sets it).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -79,3 +85,43 @@ def test_exact_gp_config3_full_size(handle):
     assert abs(nll - want) <= 1e-10 * abs(want), (nll, want)
     # value on which the recursive 1-GPU and the block-cyclic 2-GPU factorisations agreed to 3e-13
     assert abs(nll - (-64227.1208743)) <= RTOL * 64227.0, nll
+
+
+@pytest.mark.skipif(os.environ.get("AB_RUN_UNVERIFIED") != "1",
+                    reason="not yet run on a GPU (round-1 budget spent); enabled by tools/gpu_r2_visit1.sh")
+def test_loo_cv_config4_full_size(handle):
+    n = 32768
+    handle.trim()
+    ops, pp = prog(6)
+    x = np.random.default_rng(27).uniform(0.0, 10.0, size=n)  # bench_utils.h:76-85 shape, seed 27
+    y = targets(x)
+    f, info = handle.gp_fit(ops, pp, x.reshape(-1, 1), y)
+    assert f.is_positive_definite()
+    # pure leave-one-out (LeaveOneOutGrouper): mean_i = y_i - alpha_i / (K^-1)_ii, var_i = 1 / (K^-1)_ii
+    _, off, idx = capi.group_indexers(np.arange(n))
+    mean, var, _, _ = handle.gp_cv(f, y, info, off, idx, capi.MARGINAL)
+    sample = np.array([0, 1, 63, 64, 4095, 12345, 20000, n - 2, n - 1])
+    E = np.zeros((n, len(sample)))
+    E[sample, np.arange(len(sample))] = 1.0
+    Kinv_cols = f.solve(E)
+    d = Kinv_cols[sample, np.arange(len(sample))]
+    assert_close(var[sample], 1.0 / d, 1e-8, "LOO variance")
+    assert_close(mean[sample], y[sample] - info[sample] / d, 1e-8, "LOO mean")
+    # leave-one-group-out, grouper int(x) % 8 (bench_loo_cv.cc:95-105): for each group g
+    #   (K^-1)_gg (y_g - mean_g) = alpha_g, checked with one solve per group
+    keys = x.astype(np.int64) % 8
+    gk, goff, gidx = capi.group_indexers(keys)
+    assert list(gk) == sorted(set(keys.tolist()))               # std::map key order
+    assert np.array_equal(np.sort(gidx), np.arange(n))           # a permutation
+    for g in range(len(gk)):                                     # encounter order inside a group
+        members = gidx[goff[g]:goff[g + 1]]
+        assert np.array_equal(members, np.flatnonzero(keys == gk[g]))
+    gmean, gvar, _, _ = handle.gp_cv(f, y, info, goff, gidx, capi.MARGINAL)
+    assert np.all(gvar > 0.0)
+    for g in (0, len(gk) - 1):
+        members = gidx[goff[g]:goff[g + 1]]
+        r = np.zeros(n)
+        r[members] = y[members] - gmean[members]
+        z = f.solve(r.reshape(-1, 1)).ravel()
+        assert_close(z[members], info[members], 1e-7, f"group {g} conditional mean")
+    f.free()
