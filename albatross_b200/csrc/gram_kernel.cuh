@@ -77,6 +77,12 @@ constexpr int GRAM_THREADS = 256;
 #ifndef AB_GRAM_OFF32
 #define AB_GRAM_OFF32 0
 #endif
+//   AB_GRAM_UCONST   the four exp constants whose low words are not zero come from constant memory (read
+//                    through uniform registers, loaded once) instead of being re-materialised with
+//                    IMAD.MOV / UMOV pairs in every pass (ptxas does that under the 128-register cap)
+#ifndef AB_GRAM_UCONST
+#define AB_GRAM_UCONST 0
+#endif
 
 // res * 2^(m >> SHIFT) for a normal result (no overflow: the argument range is checked)
 template <int SHIFT> __device__ __forceinline__ double exp_scale(double res, int m) {
@@ -89,6 +95,15 @@ template <int SHIFT> __device__ __forceinline__ double exp_scale(double res, int
                           __double2loint(res));
 #endif
 }
+
+#if AB_GRAM_UCONST
+// {2048/ln2, -ln2/2048 high part, -ln2/2048 low part, 1/6}
+static __constant__ double EXP_BIG_K[4] = {2954.639443740597, -0x1.62e42fef00000p-12,
+                                           -0x1.473de6af278edp-45, 0.16666666666666666};
+#define AB_EXPK(i, literal) EXP_BIG_K[i]
+#else
+#define AB_EXPK(i, literal) (literal)
+#endif
 
 // exp(x) for -708 <= x <= -0 (the argument of every radial kernel): x = (128 n + j) ln2/128 + r,
 // exp(x) = 2^n T[j] (1 + r + ... + r^5/120), |r| <= ln2/256; 10 FP64-pipe instructions, <= 1 ulp.
@@ -117,12 +132,12 @@ __device__ __forceinline__ double exp_core(double x, const double *__restrict__ 
 // <= 1.3 ulp (tools/make_exp_table.py generates both tables).
 __device__ __forceinline__ double exp_core_big(double x, const double *__restrict__ tab,
                                                int &hi_max) {
-  const double t = fma(x, 2954.639443740597, 6755399441055744.0); // x * 2048/ln2
+  const double t = fma(x, AB_EXPK(0, 2954.639443740597), 6755399441055744.0); // x * 2048/ln2
   const int m = __double2loint(t);
   const double mf = t - 6755399441055744.0;
-  double r = fma(mf, -0x1.62e42fef00000p-12, x);
-  r = fma(mf, -0x1.473de6af278edp-45, r);
-  const double p = fma(r, 0.16666666666666666, 0.5);
+  double r = fma(mf, AB_EXPK(1, -0x1.62e42fef00000p-12), x);
+  r = fma(mf, AB_EXPK(2, -0x1.473de6af278edp-45), r);
+  const double p = fma(r, AB_EXPK(3, 0.16666666666666666), 0.5);
 #if AB_GRAM_QFORM
   const double q = r * fma(r, p, 1.); // expm1(r)
 #else
