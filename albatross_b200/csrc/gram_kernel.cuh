@@ -566,8 +566,46 @@ template <int K0, int K1, int K2, int TAB = FIXED_TABLE> struct EvalFixed {
 #endif
 constexpr unsigned SB = AB_GRAM_SB;
 
+// AB_GRAM_MICRO (round-2 candidate; tools/sweep.sh k_r2_micro builds gram.cu and gram_fixed.cu with it):
+// a CTA takes the four tiles of a 2 x 2 micro-block one after the other — (2I, 2J), (2I+1, 2J),
+// (2I, 2J+1), (2I+1, 2J+1) — so that its consecutive direct tiles extend the same 64 columns (and its
+// consecutive mirror tiles the same 64 columns of the upper triangle) by the next 512 bytes: the store
+// pattern of a 128 x 128 tile (pure-store probe: 5223 vs 4993 GB/s, profiles/r01c_store_pattern.txt) and
+// half the 2 MB pages per byte written, with the 64 x 64 kernel body unchanged.  Work item t = 4 *
+// micro-block + sub-tile; micro-blocks are walked in the super-block order below at half resolution.
+#ifndef AB_GRAM_MICRO
+#define AB_GRAM_MICRO 0
+#endif
+template <bool SYM> constexpr bool micro_blocks() { return SYM && AB_GRAM_MICRO != 0; }
+
+// First work item of a CTA and the one after t (grid of G CTAs).
+template <bool SYM> __device__ __forceinline__ unsigned first_item(unsigned cta) {
+  return micro_blocks<SYM>() ? 4u * cta : cta;
+}
+template <bool SYM> __device__ __forceinline__ unsigned advance_item(unsigned t, unsigned G) {
+  if (micro_blocks<SYM>()) {
+    return (t & 3u) != 3u ? t + 1u : t + 4u * G - 3u;
+  }
+  return t + G;
+}
+
 template <bool SYM>
 __device__ __forceinline__ bool decode_tile(unsigned t, unsigned tiles_i, unsigned &I, unsigned &J) {
+  if (micro_blocks<SYM>()) {
+    const unsigned micro = t >> 2, sub = t & 3u;
+    const unsigned sb = micro / (SB * SB);
+    const unsigned local = micro % (SB * SB);
+    unsigned i = static_cast<unsigned>((sqrtf(8.f * static_cast<float>(sb) + 1.f) - 1.f) * 0.5f);
+    while (i * (i + 1u) / 2u > sb) {
+      --i;
+    }
+    while ((i + 1u) * (i + 2u) / 2u <= sb) {
+      ++i;
+    }
+    I = 2u * (i * SB + local % SB) + (sub & 1u);
+    J = 2u * ((sb - i * (i + 1u) / 2u) * SB + local / SB) + (sub >> 1);
+    return I < tiles_i && J <= I;
+  }
   if (SYM) {
     const unsigned sb = t / (SB * SB);
     const unsigned local = t % (SB * SB);
@@ -592,7 +630,7 @@ template <bool SYM>
 __device__ __forceinline__ unsigned next_tile(unsigned t, unsigned step, unsigned nitems,
                                               unsigned tiles_i, unsigned &I, unsigned &J) {
   while (t < nitems && !decode_tile<SYM>(t, tiles_i, I, J)) {
-    t += step;
+    t = advance_item<SYM>(t, step);
   }
   return t;
 }
@@ -601,6 +639,11 @@ __device__ __forceinline__ unsigned next_tile(unsigned t, unsigned step, unsigne
 inline int64_t gram_items(bool sym, int64_t tiles_i, int64_t tiles_j) {
   if (!sym) {
     return tiles_i * tiles_j;
+  }
+  if (AB_GRAM_MICRO != 0) { // micro-blocks of 2 x 2 tiles, four work items each
+    const int64_t mt = (tiles_i + 1) / 2;
+    const int64_t nsb = (mt + SB - 1) / SB;
+    return nsb * (nsb + 1) / 2 * SB * SB * 4;
   }
   const int64_t nsb = (tiles_i + SB - 1) / SB;
   return nsb * (nsb + 1) / 2 * SB * SB;
@@ -783,7 +826,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   const double *tab = TABLE_IN_SMEM ? EV::lane_table(gram_smem, lane) : EV::table();
   const bool need_dist = DIM != 1 && EV::need_dist(P);
 
-  unsigned t = blockIdx.x;
+  unsigned t = first_item<SYM>(blockIdx.x);
   unsigned I = 0, J = 0;
   double px[FEAT_SLOTS], py[FEAT_SLOTS];
   t = next_tile<SYM>(t, gridDim.x, ntiles, static_cast<unsigned>(tiles_i), I, J);
@@ -827,7 +870,8 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
     __syncthreads();
 
     // prefetch the next tile's features; they are consumed at the top of the next iteration
-    t = next_tile<SYM>(t + gridDim.x, gridDim.x, ntiles, static_cast<unsigned>(tiles_i), I, J);
+    t = next_tile<SYM>(advance_item<SYM>(t, gridDim.x), gridDim.x, ntiles,
+                       static_cast<unsigned>(tiles_i), I, J);
     if (t < ntiles) {
       fetch_features<DIM>(fx, ldfx, n, fy, ldfy, m, I, J, tid, px, py);
     }
@@ -1054,7 +1098,8 @@ inline cudaError_t gram_launch(ab_handle_s *h, const DevProg &P, const double *f
     configured = true;
   }
   const int64_t resident = static_cast<int64_t>(MINB) * h->sm_count;
-  const unsigned grid = static_cast<unsigned>(ntiles < resident ? ntiles : resident);
+  const int64_t units = micro_blocks<SYM>() ? ntiles / 4 : ntiles; // what a CTA strides over
+  const unsigned grid = static_cast<unsigned>(units < resident ? units : resident);
   gram_kernel<DIM, SYM, EV, COLS, MINB><<<grid, GRAM_THREADS, smem, h->stream>>>(
       P, fx, ldfx, n, fy, ldfy, m, out, ld, tiles_i, ntiles, flags);
   return cudaGetLastError();
