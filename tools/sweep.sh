@@ -67,6 +67,9 @@ for v in "${VARIANTS[@]}"; do
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | tee -a $LOG
     if [ "$tag" = "p_nb2048" ]; then
+      # wide-row GEMV candidate (run-time switch): parity of the solve paths, then the solve_ms column
+      AB_GEMV_WIDE=1 timeout 200 python -m pytest tests/test_gpu_gp.py -m gpu -q -x 2>&1 | tail -2 | sed 's/^/gemv_wide: /' | tee -a $LOG
+      AB_GEMV_WIDE=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | sed 's/^/gemv_wide: /' | tee -a $LOG
       AB_POTRF_RECURSIVE=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | sed 's/^/recursive: /' | tee -a $LOG
     fi
   elif [ "$src" = "gemm" ]; then
