@@ -13,6 +13,8 @@
 // 10 FP64 ops, <= 1 ulp) and sqrt (MUFU.RSQ64H seed + Goldschmidt, 7 FP64 ops, <= 1 ulp).
 #include "gram_kernel.cuh"
 
+#include <cstring>
+
 #include <cmath>
 
 namespace ab {
@@ -66,12 +68,23 @@ static bool leaf_to_dev_raw(const ab_op &o, DevOp *d) {
 }
 
 static bool leaf_to_dev(const ab_op &o, DevOp *d) {
-  d->ab1 = d->ab2 = 0.;
+  d->ab1 = d->ab2 = d->a2s = d->a1s = 0.;
+  d->lim_hi = d->pad_ = 0;
   if (!leaf_to_dev_raw(o, d)) {
     return false;
   }
   d->ab1 = d->amp * d->b1;
   d->ab2 = d->amp * d->b2;
+  constexpr double steps_per_unit = 2954.639443740597; // 2048 / ln 2
+  d->a2s = d->a2 * steps_per_unit;
+  d->a1s = d->a1 * steps_per_unit;
+  const double a = (d->flags & DF_USES_DIST) ? d->a1 : d->a2;
+  const double limit = a < 0. ? 708. / -a : 0.;          // a >= 0 cannot occur for a live radial leaf
+  uint64_t bits = 0;
+  std::memcpy(&bits, &limit, sizeof bits);
+  const int64_t hi = static_cast<int64_t>(bits >> 32) - 1; // one high-word step below the limit
+  d->lim_hi = (limit > 0. && limit < 1e300 && hi > 0) ? static_cast<int>(hi) : 0;
+  d->pad_ = 0;
   return true;
 }
 

@@ -35,6 +35,11 @@ struct DevOp {
   int flags;
   double a2, a1, b2, b1, amp;
   double ab1, ab2; // amp * b1, amp * b2 (AB_GRAM_AMPFOLD: amplitude folded into the polynomial)
+  // AB_GRAM_SCALEDEXP: a2 * 2048/ln2, a1 * 2048/ln2, and the high word of the largest argument
+  // (d^2 resp. d) for which a * arg >= -708, rounded down (conservative)
+  double a2s, a1s;
+  int lim_hi;
+  int pad_;
 };
 
 // mode 0: "sum of products" — expr := term (+ term)*, term := leaf (* leaf)*, evaluated left to

@@ -83,6 +83,16 @@ constexpr int GRAM_THREADS = 256;
 #ifndef AB_GRAM_UCONST
 #define AB_GRAM_UCONST 0
 #endif
+//   AB_GRAM_SCALEDEXP  range reduction in table steps straight from the distance: with as = a * 2048/ln2
+//                    (host side), t = fma(d, as, magic), r' = fma(d, as, -m) (one rounding, |r'| <= 1/2),
+//                    exp = 2^(m/2048) (1 + r' (c1 + r' (c2 + r' c3))): 7 FP64 instructions per exp instead of
+//                    9 (no a * d product, one reduction step).  Same error bound against the exact
+//                    exp(a d) as the two-step reduction, 1.57 (1 + |x|) 2^-53 (CPU emulation, 2e7 samples),
+//                    but up to 2 |x| 2^-53 away from libm's exp(fl(a d)), i.e. from the reference's last bits.
+//                    The range check moves to the distance (unsigned high word against a host-side limit).
+#ifndef AB_GRAM_SCALEDEXP
+#define AB_GRAM_SCALEDEXP 0
+#endif
 
 // res * 2^(m >> SHIFT) for a normal result (no overflow: the argument range is checked)
 template <int SHIFT> __device__ __forceinline__ double exp_scale(double res, int m) {
@@ -182,6 +192,29 @@ __device__ __forceinline__ double exp_patch(double x, double fast) {
   // subnormal < 3e-308 or 0, flushed to 0 here; NaN propagates.  x > 0 cannot occur: every radial
   // argument is (negative coefficient) * (distance >= 0).
   return (x < -708.0) ? 0. : ((x != x) ? x : fast);
+}
+
+// AB_GRAM_SCALEDEXP: exp(a d) from d and as = a * 2048/ln2, for 0 <= d <= 708 / |a| (checked by the caller).
+static __constant__ double EXP_SCALED_C[3] = {0x1.62e42fefa39efp-12,                       // ln2/2048
+                                              0x1.62e42fefa39efp-12 * 0x1.62e42fefa39efp-12 * 0.5,
+                                              0x1.62e42fefa39efp-12 * 0x1.62e42fefa39efp-12 *
+                                                  0x1.62e42fefa39efp-12 / 6.0};
+__device__ __forceinline__ double exp_scaled(double d, double as, const double *__restrict__ tab) {
+  const double t = fma(d, as, 6755399441055744.0);
+  const int m = __double2loint(t);
+  const double mf = t - 6755399441055744.0;
+  const double r = fma(d, as, -mf); // in table steps, exact up to one rounding
+  double u = fma(r, EXP_SCALED_C[2], EXP_SCALED_C[1]);
+  u = fma(r, u, EXP_SCALED_C[0]);
+  const double q = r * u; // expm1(r ln2/2048)
+  const double tj = tab[m & 2047];
+  const double res = fma(tj, q, tj);
+  return exp_scale<11>(res, m);
+}
+// the same for a single lane whose distance is outside the fast range (cold path)
+static __device__ __noinline__ double exp_scaled_special(double d, double a) {
+  const double x = a * d;
+  return (x < -708.0) ? 0. : ((x != x) ? x : exp(x));
 }
 
 // sqrt(a) for positive normal a: MUFU.RSQ64H seed (~2^-22) + one Goldschmidt step on g ~ sqrt(a)
@@ -424,6 +457,30 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
     }
   } else {
     double v[NP], e[NP];
+#if AB_GRAM_SCALEDEXP
+    static_assert(TAB == TAB_2048, "AB_GRAM_SCALEDEXP uses the 2048-entry table");
+    {
+      const double as = KIND == LS_SE ? o.a2s : o.a1s;
+      const unsigned lim = static_cast<unsigned>(o.lim_hi);
+      unsigned worst = 0u;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        v[i] = KIND == LS_SE ? d2[i] : dist[i];
+        const unsigned hi = static_cast<unsigned>(__double2hiint(v[i]));
+        if constexpr (CHECK) { // per lane: the same bits as the branch-free path when in range
+          e[i] = hi <= lim ? exp_scaled(v[i], as, tab)
+                           : exp_scaled_special(v[i], KIND == LS_SE ? o.a2 : o.a1);
+        } else {
+          e[i] = exp_scaled(v[i], as, tab);
+          worst = max(worst, hi);
+        }
+      }
+      if constexpr (!CHECK) {
+        // fold into the caller's signed accumulator: any value above EXP_HI_LIMIT means "re-evaluate"
+        hi_acc = max(hi_acc, worst > lim ? 0x7fffffff : EXP_HI_LIMIT);
+      }
+    }
+#else
     if constexpr (KIND == LS_SE) {
       const double a2 = o.a2;
 #pragma unroll
@@ -442,6 +499,7 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
     } else {
       exp_batch_nocheck<NP, TAB>(v, tab, e, hi_acc);
     }
+#endif
     const double amp = o.amp;
 #if AB_GRAM_AMPFOLD
     if constexpr (KIND == LS_M32 || KIND == LS_M52) {
