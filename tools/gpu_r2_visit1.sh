@@ -3,6 +3,8 @@
 # leg has its own timeout and writes to gpurun_out/ as it goes, so a cut-off call still leaves
 # results.  Usage (under gpurun): bash tools/gpu_r2_visit1.sh [tag] [deadline_seconds]
 set -u
+# BEFORE calling gpurun: `bash tools/sweep.sh build` here (3 min of CPU; the variant libraries travel with the
+# snapshot).  Nothing is compiled on the GPU box.
 TAG=${1:-r02a}
 DEADLINE=${2:-1500}
 OUT=gpurun_out
