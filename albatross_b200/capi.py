@@ -17,6 +17,19 @@ LIB_PATH = os.environ.get("ALBATROSS_B200_LIB") or os.path.join(HERE, "csrc", "l
 
 # opcodes (include/albatross_b200.h)
 SE, EXP, M32, M52, CONST, NOISE, SUM, PROD = 1, 2, 3, 4, 5, 6, 7, 8
+
+
+def bench_program(name):
+    """(ops, params) of the postfix programs BASELINE.json's configs use (timing tools / bench):
+    "se_noise" = SE(1, 1) + IndependentNoise(0.1) (configs[2..4]); "se_m52" = SE(2, 1.5) + Matern52(3, 0.7)
+    (configs[1]); "se_m52_noise" = the latter + IndependentNoise(0.1)."""
+    if name == "se_noise":
+        return [SE, NOISE, SUM], [1.0, 1.0, 0.1, 0.0, 0.0, 0.0]
+    if name == "se_m52":
+        return [SE, M52, SUM], [2.0, 1.5, 3.0, 0.7, 0.0, 0.0]
+    if name == "se_m52_noise":
+        return [SE, M52, SUM, NOISE, SUM], [2.0, 1.5, 3.0, 0.7, 0.0, 0.0, 0.1, 0.0, 0.0, 0.0]
+    raise ValueError(name)
 MEAN, MARGINAL, JOINT = 0, 1, 2
 GRAM_FULL, GRAM_LOWER_ONLY = 0, 1
 

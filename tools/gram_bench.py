@@ -5,7 +5,6 @@ import numpy as np
 
 sys.path.insert(0, ".")
 from albatross_b200 import capi  # noqa: E402
-from oracle.oracle import menu_program  # noqa: E402
 
 PARAMS = {4: [1.3], 0: [2.0, 1.5], 3: [3.0, 0.7], 6: [1.0, 1.0, 0.1], 7: [2.0, 1.5, 3.0, 0.7],
           8: [2.0, 1.5, 3.0, 0.7, 0.1], 9: [2.0, 1.5, 3.0, 0.7, 1.1, 0.9, 1.2, 0.3]}
@@ -19,7 +18,15 @@ def main():
     flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     cross = len(sys.argv) > 6 and sys.argv[6] == "cross"
     h = capi.Handle(0)
-    ops, pp = menu_program(cid, PARAMS[cid])
+    if cid == 7:
+        ops, pp = capi.bench_program("se_m52")
+    elif cid == 8:
+        ops, pp = capi.bench_program("se_m52_noise")
+    elif cid == 6:
+        ops, pp = capi.bench_program("se_noise")
+    else:  # other menu entries: the test helper's program builder (development use only)
+        from oracle.oracle import menu_program
+        ops, pp = menu_program(cid, PARAMS[cid])
     x = np.random.default_rng(0).uniform(0, 10, size=(n, dim))
     fd = h.upload_features(x)
     flush = h.alloc(8192, 8192)  # 512 MiB > L2

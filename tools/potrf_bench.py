@@ -6,14 +6,13 @@ import numpy as np
 
 sys.path.insert(0, ".")
 from albatross_b200 import capi  # noqa: E402
-from oracle.oracle import menu_program  # noqa: E402
 
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     h = capi.Handle(0)
-    ops, pp = menu_program(6, [1.0, 1.0, 0.1])
+    ops, pp = capi.bench_program("se_noise")
     x = np.random.default_rng(0).uniform(0, 10, size=(n, 3))
     y = np.sin(x[:, 0])
     best = {}
