@@ -53,6 +53,8 @@ constexpr int MF = WTM / 8;       // fragments per warp along m / n
 constexpr int NF = WTN / 8;
 static_assert(BM % (8 * WARPS_M) == 0 && BN % (8 * WARPS_N) == 0 && BK % 4 == 0, "tile shape");
 static_assert((BK * BM / 2) % GEMM_THREADS == 0 && (BK * BN / 2) % GEMM_THREADS == 0, "loader shape");
+// the in-place triangular-solve leaves (linalg.cuh) need one CTA to own a whole LEAF-wide operand
+static_assert(BN >= LEAF && BM >= LEAF, "CTA tile smaller than the in-place solve leaf");
 constexpr int LDK = BK + 4; // [extent][LDK] tile of an operand whose k index is contiguous in memory
 // [BK][extent + 4] tile of an operand whose m/n index is contiguous in memory
 template <int EXTENT, bool KMAJOR> constexpr int tile_elems() {

@@ -22,8 +22,9 @@ enum GemmFlags : unsigned {
 
 // C[m x n] = alpha * op(A) * op(B) + beta * C.   beta == 0 never reads C.
 // In-place use (C aliasing A or B) is allowed only when one CTA owns the whole aliased extent:
-// C == A with n <= 128 and k == n (right-multiplication by a small matrix), or C == B with
-// m <= 128 and k == m (left-multiplication).
+// C == A with n <= 64 (= the CTA tile's BN) and k == n (right-multiplication by a small matrix), or
+// C == B with m <= 128 (= BM) and k == m (left-multiplication).  The callers are the LEAF = 64 wide
+// triangular-solve leaves.
 int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double alpha, MatView A,
          MatView B, double beta, MatView C);
 
