@@ -72,3 +72,18 @@ def test_group_indexers_bit_exact(golden):
     want = Restate.group_indexers(group_keys(x, 1, 8))
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+
+
+def test_bench_programs_match_the_test_menu():
+    """capi.bench_program (what the timing tools and bench.py feed the library) builds the same postfix
+    programs as the oracle-side menu used by the parity tests."""
+    from oracle.oracle import menu_program
+
+    def same(a, b):
+        return list(a[0]) == list(b[0]) and [float(v) for v in a[1]] == [float(v) for v in b[1]]
+
+    assert same(capi.bench_program("se_noise"), menu_program(6, [1.0, 1.0, 0.1]))
+    assert same(capi.bench_program("se_m52"), menu_program(7, [2.0, 1.5, 3.0, 0.7]))
+    assert same(capi.bench_program("se_m52_noise"), menu_program(8, [2.0, 1.5, 3.0, 0.7, 0.1]))
+    with pytest.raises(ValueError):
+        capi.bench_program("nope")
