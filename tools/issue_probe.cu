@@ -129,6 +129,72 @@ __global__ void dfma3_kernel(double *out, int iters, double a, long long *cycles
   }
 }
 
+// Do DMMA (FP64 tensor sub-pipe) and DFMA (FP64 pipe) share hardware?  ND independent m8n8k4 accumulators
+// and NF independent DFMA chains per thread; if the two are separate units the mixed loop costs
+// max(ND * 16, NF * 2) cycles per iteration and sub-partition, if they are one unit the sum.
+template <int ND, int NF>
+__global__ void dmma_dfma_kernel(double *out, int iters, double a, long long *cycles) {
+  double d[ND > 0 ? ND : 1][2], f[NF > 0 ? NF : 1];
+#pragma unroll
+  for (int i = 0; i < (ND > 0 ? ND : 1); ++i) {
+    d[i][0] = threadIdx.x * 1e-3 + i;
+    d[i][1] = threadIdx.x * 2e-3 + i;
+  }
+#pragma unroll
+  for (int i = 0; i < (NF > 0 ? NF : 1); ++i) {
+    f[i] = threadIdx.x * 1e-3 + i;
+  }
+  const double fa = 1.0 + a * 1e-9 * threadIdx.x, fb = 0.999 + a * 1e-9;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < (ND > NF ? ND : NF); ++i) {
+      if (i < ND) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                     : "+d"(d[i][0]), "+d"(d[i][1])
+                     : "d"(fa), "d"(fb));
+      }
+      if (i < NF) {
+        f[i] = fma(f[i], a, a);
+      }
+    }
+  }
+  const long long t1 = clock64();
+  double s = 0.;
+#pragma unroll
+  for (int i = 0; i < (ND > 0 ? ND : 1); ++i) {
+    s += d[i][0] + d[i][1];
+  }
+#pragma unroll
+  for (int i = 0; i < (NF > 0 ? NF : 1); ++i) {
+    s += f[i];
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    *cycles = t1 - t0;
+  }
+}
+
+template <int ND, int NF> static void run_mix(int threads, double *out, long long *cyc) {
+  const int iters = 4096;
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  for (int rep = 0; rep < 2; ++rep) {
+    dmma_dfma_kernel<ND, NF><<<sms, threads>>>(out, iters, 0.999, cyc);
+    CK(cudaDeviceSynchronize());
+  }
+  long long c = 0;
+  CK(cudaMemcpy(&c, cyc, sizeof c, cudaMemcpyDeviceToHost));
+  const double w = threads / 128.0;
+  printf("DMMA x%d + DFMA x%d per thread-iteration, warps/SMSP=%.0f : %8.2f cycles per iteration per SMSP "
+         "(separate units: %d, one unit: %d)\n",
+         ND, NF, w, c / (double)iters, (int)(w * (ND * 16 > NF * 2 ? ND * 16 : NF * 2)),
+         (int)(w * (ND * 16 + NF * 2)));
+  fflush(stdout);
+}
+
 template <int NF> static void run3(int threads, double *out, long long *cyc) {
   const int iters = 2048;
   int sms = 0;
@@ -211,6 +277,12 @@ int main() {
   run3<4>(512, out, cyc);
   run3<8>(512, out, cyc);
   run3<4>(768, out, cyc);
+  printf("-- DMMA and DFMA: one unit or two?\n");
+  run_mix<8, 0>(512, out, cyc);
+  run_mix<0, 64>(512, out, cyc);
+  run_mix<8, 64>(512, out, cyc);
+  run_mix<8, 32>(512, out, cyc);
+  run_mix<8, 16>(512, out, cyc);
   printf("issue_probe rc=0\n");
   return 0;
 }
