@@ -3,7 +3,8 @@
 # leg has its own timeout and writes to gpurun_out/ as it goes, so a cut-off call still leaves
 # results.  Usage (under gpurun): bash tools/gpu_r2_visit1.sh [tag] [deadline_seconds]
 set -u
-# BEFORE calling gpurun: `bash tools/sweep.sh build` here (3 min of CPU; the variant libraries travel with the
+# BEFORE calling gpurun: `nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/issue_probe tools/issue_probe.cu` and
+# `bash tools/sweep.sh build` here (3 min of CPU; the variant libraries travel with the
 # snapshot).  Nothing is compiled on the GPU box.
 TAG=${1:-r02a}
 DEADLINE=${2:-1500}
@@ -28,6 +29,7 @@ leg() { # leg <max seconds> <name> <command...>: skipped when the deadline is to
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 
 leg 300 pytest bash -c "AB_RUN_UNVERIFIED=1 python -m pytest tests -m gpu -q --durations=5 2>&1 | tail -30 | tee $OUT/${TAG}_pytest.log"
+leg 60 issue_probe bash -c "tools/issue_probe 2>&1 | tee $OUT/${TAG}_issue_probe.txt | tail -8"
 leg 420 configs bash -c "python tools/bench_configs.py ${TAG} 2>&1 | tail -12 | cut -c1-1500"
 leg 240 sweep_gram env SWEEP_ONLY='k_*' SWEEP_TEST="tests/test_gpu_gram.py" bash tools/sweep.sh run ${TAG}_gram
 leg 400 sweep_gemm env SWEEP_ONLY='g_*' bash tools/sweep.sh run ${TAG}_gemm
