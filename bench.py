@@ -378,6 +378,19 @@ def run_device_dist(args):
         torch.cuda.synchronize()
 
     n = args.dist_n
+    # preflight (rank-symmetric, before any collective of the library): the block-column-cyclic shard, the
+    # two packed panel buffers and 6 GB of slack must fit the free HBM of every rank, else halve N
+    nb_eff = args.nb or 1024
+    while n > 8192:
+        nblk = (n + nb_eff - 1) // nb_eff
+        need = 8.0 * n * ((nblk + world - 1) // world) * nb_eff + 2 * 8.0 * n * nb_eff + 6e9
+        free_b, _ = torch.cuda.mem_get_info()
+        if abd.max_over_ranks(1.0 if need > free_b else 0.0) == 0.0:
+            break
+        if rank == 0:
+            print(f"bench.py: N={n} needs {need / 1e9:.0f} GB per rank, {free_b / 1e9:.0f} GB free: "
+                  f"halving N", file=sys.stderr)
+        n //= 2
     x, y = make_data(n, seed=0)  # identical on every rank: features are replicated, K is sharded
     xp = torch.from_numpy(x).pin_memory().numpy()
     yp = torch.from_numpy(y).pin_memory().numpy()
