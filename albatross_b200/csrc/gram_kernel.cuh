@@ -625,24 +625,28 @@ template <int K0, int K1, int K2, int TAB = FIXED_TABLE> struct EvalFixed {
 constexpr unsigned SB = AB_GRAM_SB;
 
 // AB_GRAM_MICRO (round-2 candidate; tools/sweep.sh k_r2_micro builds gram.cu and gram_fixed.cu with it):
-// a CTA takes the four tiles of a 2 x 2 micro-block one after the other — (2I, 2J), (2I+1, 2J),
-// (2I, 2J+1), (2I+1, 2J+1) — so that its consecutive direct tiles extend the same 64 columns (and its
-// consecutive mirror tiles the same 64 columns of the upper triangle) by the next 512 bytes: the store
-// pattern of a 128 x 128 tile (pure-store probe: 5223 vs 4993 GB/s, profiles/r01c_store_pattern.txt) and
-// half the 2 MB pages per byte written, with the 64 x 64 kernel body unchanged.  Work item t = 4 *
-// micro-block + sub-tile; micro-blocks are walked in the super-block order below at half resolution.
+// a CTA takes the MB x MB tiles of a micro-block one after the other, rows fastest — for MB = 2: (2I, 2J),
+// (2I+1, 2J), (2I, 2J+1), (2I+1, 2J+1) — so that its consecutive direct tiles extend the same 64 columns
+// (and its mirror tiles the same 64 columns of the upper triangle) by the next 512 bytes: the store
+// pattern of a 128 x 128 (MB = 4: 256 x 256) tile (pure-store probe: 5223 / 5440 vs 4993 GB/s,
+// profiles/r01c_store_pattern.txt) and 1/MB of the 2 MB pages per byte written, with the 64 x 64 kernel
+// body unchanged.  Work item t = MB^2 * micro-block + sub-tile; micro-blocks are walked in the
+// super-block order below at 1/MB resolution.
 #ifndef AB_GRAM_MICRO
-#define AB_GRAM_MICRO 0
+#define AB_GRAM_MICRO 0 // 0 = off; 2 or 4 = micro-block edge MB in tiles (MB * MB work items per micro-block)
 #endif
+static_assert(AB_GRAM_MICRO == 0 || AB_GRAM_MICRO == 2 || AB_GRAM_MICRO == 4, "micro-block edge");
+constexpr unsigned MICRO_MB = AB_GRAM_MICRO == 0 ? 1u : static_cast<unsigned>(AB_GRAM_MICRO);
+constexpr unsigned MICRO_ITEMS = MICRO_MB * MICRO_MB;
 template <bool SYM> constexpr bool micro_blocks() { return SYM && AB_GRAM_MICRO != 0; }
 
 // First work item of a CTA and the one after t (grid of G CTAs).
 template <bool SYM> __device__ __forceinline__ unsigned first_item(unsigned cta) {
-  return micro_blocks<SYM>() ? 4u * cta : cta;
+  return micro_blocks<SYM>() ? MICRO_ITEMS * cta : cta;
 }
 template <bool SYM> __device__ __forceinline__ unsigned advance_item(unsigned t, unsigned G) {
   if (micro_blocks<SYM>()) {
-    return (t & 3u) != 3u ? t + 1u : t + 4u * G - 3u;
+    return (t % MICRO_ITEMS) != MICRO_ITEMS - 1u ? t + 1u : t + MICRO_ITEMS * G - (MICRO_ITEMS - 1u);
   }
   return t + G;
 }
@@ -650,7 +654,7 @@ template <bool SYM> __device__ __forceinline__ unsigned advance_item(unsigned t,
 template <bool SYM>
 __device__ __forceinline__ bool decode_tile(unsigned t, unsigned tiles_i, unsigned &I, unsigned &J) {
   if (micro_blocks<SYM>()) {
-    const unsigned micro = t >> 2, sub = t & 3u;
+    const unsigned micro = t / MICRO_ITEMS, sub = t % MICRO_ITEMS;
     const unsigned sb = micro / (SB * SB);
     const unsigned local = micro % (SB * SB);
     unsigned i = static_cast<unsigned>((sqrtf(8.f * static_cast<float>(sb) + 1.f) - 1.f) * 0.5f);
@@ -660,8 +664,8 @@ __device__ __forceinline__ bool decode_tile(unsigned t, unsigned tiles_i, unsign
     while ((i + 1u) * (i + 2u) / 2u <= sb) {
       ++i;
     }
-    I = 2u * (i * SB + local % SB) + (sub & 1u);
-    J = 2u * ((sb - i * (i + 1u) / 2u) * SB + local / SB) + (sub >> 1);
+    I = MICRO_MB * (i * SB + local % SB) + sub % MICRO_MB;
+    J = MICRO_MB * ((sb - i * (i + 1u) / 2u) * SB + local / SB) + sub / MICRO_MB;
     return I < tiles_i && J <= I;
   }
   if (SYM) {
@@ -698,10 +702,10 @@ inline int64_t gram_items(bool sym, int64_t tiles_i, int64_t tiles_j) {
   if (!sym) {
     return tiles_i * tiles_j;
   }
-  if (AB_GRAM_MICRO != 0) { // micro-blocks of 2 x 2 tiles, four work items each
-    const int64_t mt = (tiles_i + 1) / 2;
+  if (AB_GRAM_MICRO != 0) { // micro-blocks of MB x MB tiles, MB^2 work items each
+    const int64_t mt = (tiles_i + MICRO_MB - 1) / MICRO_MB;
     const int64_t nsb = (mt + SB - 1) / SB;
-    return nsb * (nsb + 1) / 2 * SB * SB * 4;
+    return nsb * (nsb + 1) / 2 * SB * SB * MICRO_ITEMS;
   }
   const int64_t nsb = (tiles_i + SB - 1) / SB;
   return nsb * (nsb + 1) / 2 * SB * SB;
@@ -1156,7 +1160,7 @@ inline cudaError_t gram_launch(ab_handle_s *h, const DevProg &P, const double *f
     configured = true;
   }
   const int64_t resident = static_cast<int64_t>(MINB) * h->sm_count;
-  const int64_t units = micro_blocks<SYM>() ? ntiles / 4 : ntiles; // what a CTA strides over
+  const int64_t units = micro_blocks<SYM>() ? ntiles / MICRO_ITEMS : ntiles; // what a CTA strides over
   const unsigned grid = static_cast<unsigned>(units < resident ? units : resident);
   gram_kernel<DIM, SYM, EV, COLS, MINB><<<grid, GRAM_THREADS, smem, h->stream>>>(
       P, fx, ldfx, n, fy, ldfy, m, out, ld, tiles_i, ntiles, flags);

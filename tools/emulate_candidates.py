@@ -17,8 +17,9 @@ SB = 16
 
 
 def decode(t, tiles_i, micro):
+    mb = micro or 1
     if micro:
-        mic, sub = t >> 2, t & 3
+        mic, sub = t // (mb * mb), t % (mb * mb)
         sb, local = mic // (SB * SB), mic % (SB * SB)
     else:
         sb, local = t // (SB * SB), t % (SB * SB)
@@ -28,8 +29,8 @@ def decode(t, tiles_i, micro):
     while (i + 1) * (i + 2) // 2 <= sb:
         i += 1
     if micro:
-        I = 2 * (i * SB + local % SB) + (sub & 1)
-        J = 2 * ((sb - i * (i + 1) // 2) * SB + local // SB) + (sub >> 1)
+        I = mb * (i * SB + local % SB) + sub % mb
+        J = mb * ((sb - i * (i + 1) // 2) * SB + local // SB) + sub // mb
     else:
         I, J = i * SB + local % SB, (sb - i * (i + 1) // 2) * SB + local // SB
     return (I < tiles_i and J <= I), I, J
@@ -37,8 +38,8 @@ def decode(t, tiles_i, micro):
 
 def items(tiles_i, micro):
     if micro:
-        nsb = ((tiles_i + 1) // 2 + SB - 1) // SB
-        return nsb * (nsb + 1) // 2 * SB * SB * 4
+        nsb = ((tiles_i + micro - 1) // micro + SB - 1) // SB
+        return nsb * (nsb + 1) // 2 * SB * SB * micro * micro
     nsb = (tiles_i + SB - 1) // SB
     return nsb * (nsb + 1) // 2 * SB * SB
 
@@ -46,18 +47,19 @@ def items(tiles_i, micro):
 def check_walk():
     for tiles_i in (1, 2, 3, 5, 16, 17, 31, 32, 33, 100, 512):
         for G in (1, 7, 296):
-            for micro in (0, 1):
+            for micro in (0, 2, 4):  # micro-block edge MB (0 = plain order)
                 n = items(tiles_i, micro)
-                grid = min(n // 4 if micro else n, G)
+                per = micro * micro if micro else 1
+                grid = min(n // per, G)
                 seen = set()
                 for b in range(grid):
-                    t = 4 * b if micro else b
+                    t = per * b
                     while t < n:
                         ok, I, J = decode(t, tiles_i, micro)
                         if ok:
                             assert (I, J) not in seen
                             seen.add((I, J))
-                        t = (t + 1 if (t & 3) != 3 else t + 4 * grid - 3) if micro else t + grid
+                        t = (t + 1 if t % per != per - 1 else t + per * grid - (per - 1)) if micro else t + grid
                 assert seen == {(I, J) for I in range(tiles_i) for J in range(I + 1)}
     print("1. tile walks cover the lower triangle exactly once (plain and micro-block order)")
 

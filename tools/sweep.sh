@@ -19,8 +19,9 @@ VARIANTS=(
   "k_r2_all_but_off32:gram_fixed:-DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1"
   "k_r2_scaledexp:gram_fixed:-DAB_GRAM_SCALEDEXP=1"
   "k_r2_all_scaledexp:gram_fixed:-DAB_GRAM_SCALEDEXP=1 -DAB_GRAM_OFF32=1 -DAB_GRAM_AMPFOLD=1"
-  "k_r2_micro:gram_fixed,gram:-DAB_GRAM_MICRO=1"
-  "k_r2_all_micro:gram_fixed,gram:-DAB_GRAM_MICRO=1 -DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1"
+  "k_r2_micro2:gram_fixed,gram:-DAB_GRAM_MICRO=2"
+  "k_r2_micro4:gram_fixed,gram:-DAB_GRAM_MICRO=4"
+  "k_r2_all_micro:gram_fixed,gram:-DAB_GRAM_MICRO=2 -DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1"
   "k_r2_all_cols4_mb1:gram_fixed:-DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1 -DAB_GRAM_COLS=4 -DAB_GRAM_MINB=1"
   "k_r1_nocheck:gram_fixed:-DAB_GRAM_ONECHECK=0 -DAB_GRAM_EXPMAD=0"
   "p_nb2048:linalg:"
