@@ -86,6 +86,28 @@ __device__ __forceinline__ bool decode_sym(unsigned t, unsigned tiles, unsigned 
 // ORDER 0: all tiles, column-major over the tile grid.  ORDER 1: lower tiles in super-block order,
 // each followed by its mirror tile.  ORDER 2: as 1 but lower tiles only (half the bytes).
 // MECH 0: st.global WIDTH bytes/lane.  MECH 1: cp.async.bulk from shared memory.
+// ORDER 3 of the Gram candidates (AB_GRAM_MICRO): 64 x 64 lower tiles + mirrors, but each CTA walks the MB x MB
+// tiles of a micro-block one after the other (rows fastest), micro-blocks in super-block order.
+__global__ void __launch_bounds__(THREADS) micro_fill(double *out, int64_t n, int64_t ld, double v,
+                                                      unsigned SB, unsigned MB) {
+  constexpr int T = 64;
+  const unsigned tiles = static_cast<unsigned>(n / T);
+  const unsigned mt = (tiles + MB - 1) / MB;
+  const unsigned nsb = (mt + SB - 1) / SB;
+  const unsigned nmicro = nsb * (nsb + 1) / 2 * SB * SB;
+  for (unsigned mic = blockIdx.x; mic < nmicro; mic += gridDim.x) {
+    unsigned MI, MJ;
+    if (!decode_sym(mic, mt, SB, MI, MJ)) continue;
+    for (unsigned sub = 0; sub < MB * MB; ++sub) {
+      const unsigned I = MB * MI + sub % MB, J = MB * MJ + sub / MB;
+      if (I >= tiles || J > I) continue;
+      const int64_t i0 = static_cast<int64_t>(I) * T, j0 = static_cast<int64_t>(J) * T;
+      write_tile<T, 16>(out, ld, i0, j0, v);
+      if (I != J) write_tile<T, 8>(out, ld, j0, i0, v);
+    }
+  }
+}
+
 template <int T, int ORDER, int WIDTH, int MECH>
 __global__ void __launch_bounds__(THREADS) tile_fill(double *out, int64_t n, int64_t ld, double v,
                                                      unsigned SB) {
@@ -215,6 +237,12 @@ int main(int argc, char **argv) {
   run_tile<128, 1, 16, 0>(g2, 2048);
   run_tile<256, 1, 16, 0>(g2, 2048);
   run_tile<64, 2, 16, 0>(g2, 1024);
+  // micro-block order of 64 x 64 tiles (what AB_GRAM_MICRO=2 / 4 would write)
+  for (unsigned mb : {1u, 2u, 4u, 8u}) {
+    char name[96];
+    snprintf(name, sizeof name, "T=64 order=sym+mirror micro-block %ux%u grid=%d sb=16", mb, mb, g2);
+    timeit(name, 8.0 * g_n * g_n, [&] { micro_fill<<<g2, THREADS>>>(g_out, g_n, g_ld, 1.0, 16u, mb); });
+  }
   // bulk (TMA 1-D) stores from shared memory
   run_tile<64, 0, 16, 1>(g2, 1024);
   run_tile<64, 1, 16, 1>(g2, 1024);
