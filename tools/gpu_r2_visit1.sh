@@ -7,7 +7,7 @@ set -u
 # `bash tools/sweep.sh build` here (3 min of CPU; the variant libraries travel with the
 # snapshot).  Nothing is compiled on the GPU box.
 TAG=${1:-r02a}
-DEADLINE=${2:-1500}
+DEADLINE=${2:-1700}
 OUT=gpurun_out
 mkdir -p $OUT
 T0=$(date +%s)
@@ -32,7 +32,7 @@ leg 300 pytest bash -c "AB_RUN_UNVERIFIED=1 python -m pytest tests -m gpu -q --d
 leg 60 issue_probe bash -c "tools/issue_probe 2>&1 | tee $OUT/${TAG}_issue_probe.txt | tail -8"
 leg 60 store_pattern bash -c "tools/store_pattern 32768 2>&1 | tee $OUT/${TAG}_store_pattern.txt | grep micro"
 leg 420 configs bash -c "python tools/bench_configs.py ${TAG} 2>&1 | tail -12 | cut -c1-1500"
-leg 240 sweep_gram env SWEEP_ONLY='k_*' SWEEP_TEST="tests/test_gpu_gram.py" bash tools/sweep.sh run ${TAG}_gram
+leg 400 sweep_gram env SWEEP_ONLY='k_*' SWEEP_TEST="tests/test_gpu_gram.py" bash tools/sweep.sh run ${TAG}_gram
 leg 400 sweep_gemm env SWEEP_ONLY='g_*' bash tools/sweep.sh run ${TAG}_gemm
 leg 200 sweep_potrf env SWEEP_ONLY='p_*' bash tools/sweep.sh run ${TAG}_potrf
 leg 200 bench bash -c "python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; tail -c 2500 $OUT/${TAG}_bench.json"
