@@ -76,6 +76,7 @@ SYMBOLS = [
     "ab_sparse_predict", "ab_sparse_export_R",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
     "ab_dist_factor_free", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
+    "ab_partition_triangular",
 ]
 DIST_ID_BYTES = 128
 
@@ -138,6 +139,13 @@ def group_indexers(item_keys):
     _check(lib().ab_group_indexers(_i(gk), C.c_int64(n), _i(keys), _i(offsets), _i(indices),
                                    C.byref(g)))
     return keys[:g.value].copy(), offsets[:g.value + 1].copy(), indices[:n].copy()
+
+
+def partition_triangular(n, count):
+    """detail::partition_triangular (indexing/block.hpp:25-44): (count, 2) array of [start, end)."""
+    out = np.empty(2 * count, dtype=np.int64)
+    _check(lib().ab_partition_triangular(C.c_int64(n), C.c_int64(count), _i(out)))
+    return out.reshape(count, 2)
 
 
 class Matrix:

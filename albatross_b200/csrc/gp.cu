@@ -1021,4 +1021,22 @@ int ab_group_indexers(const int64_t *item_keys, int64_t n, int64_t *keys, int64_
   return AB_OK;
 }
 
+int ab_partition_triangular(int64_t n, int64_t count, int64_t *bounds) {
+  AB_REQUIRE(n >= 0 && count >= 1 && bounds != nullptr, "partition_triangular arguments");
+  // end_b = rint(n * f_b) with f_b^2 = b / count accumulated the way the reference accumulates it (the
+  // rounding of the running area is part of the contract): block.hpp:31-39
+  double area = 0.;
+  int64_t start = 0;
+  for (int64_t b = 0; b < count; ++b) {
+    const double end_fraction = std::sqrt(1. / static_cast<double>(count) + area);
+    area = end_fraction * end_fraction;
+    const int64_t end = static_cast<int64_t>(std::rint(static_cast<double>(n) * end_fraction));
+    bounds[2 * b] = start;
+    bounds[2 * b + 1] = end;
+    start = end;
+  }
+  bounds[2 * (count - 1) + 1] = std::min(bounds[2 * (count - 1) + 1], n); // block.hpp:41-42
+  return AB_OK;
+}
+
 } // extern "C"

@@ -391,6 +391,14 @@ AB_API int ab_gemm(ab_handle h, uint32_t flags, double alpha, ab_matrix A, ab_ma
 AB_API int ab_group_indexers(const int64_t *item_keys, int64_t n, int64_t *keys, int64_t *offsets,
                       int64_t *indices, int64_t *ngroups);
 
+/*
+ * detail::partition_triangular src/indexing/block.hpp:25-44: `count` row (lower-triangular) or column
+ * (upper-triangular) blocks [start, end) of an n x n triangle with approximately equal areas — what the
+ * reference's threaded Gram build hands to its pool (callers.hpp:134-166) and what a symmetric Gram build
+ * sharded over `count` GPUs uses as row ranges.  bounds receives 2 * count entries: start_0, end_0, ...
+ */
+AB_API int ab_partition_triangular(int64_t n, int64_t count, int64_t *bounds);
+
 #ifdef __cplusplus
 }
 #endif
