@@ -73,7 +73,8 @@ SYMBOLS = [
     "ab_gp_fit_nll", "ab_gp_predict", "ab_gp_cv", "ab_gp_fit_d", "ab_gp_nll_d",
     "ab_group_indexers", "ab_gemm", "ab_gp_cv_shard", "ab_gp_cv_scores", "ab_gp_predict2",
     "ab_sparse_fit", "ab_sparse_free", "ab_sparse_info", "ab_sparse_log_likelihood",
-    "ab_sparse_predict", "ab_sparse_export_R",
+    "ab_sparse_predict", "ab_sparse_export_R", "ab_sparse_fit2", "ab_sparse_log_likelihood2",
+    "ab_sparse_predict2",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
     "ab_dist_factor_free", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
     "ab_partition_triangular",
@@ -479,37 +480,45 @@ class Handle:
 
     # -- sparse GP ----------------------------------------------------------------------------
     def _sparse_args(self, ops, params, feats, y, yvar, inducing, offsets, indices,
-                     measurement_nugget, inducing_nugget):
-        prog, nops = program(ops, params)
+                     measurement_nugget, inducing_nugget, fu=None, uu=None):
+        """fu / uu: optional (ops, params) of the K_fu and K_uu programs when they differ from the
+        K_ff one (MeasurementOnly terms): the ab_sparse_*2 entry points are used then."""
+        progs = [program(ops, params)]
+        if fu is not None or uu is not None:
+            progs.append(program(*(fu if fu is not None else (ops, params))))
+            progs.append(program(*(uu if uu is not None else (ops, params))))
         x, u = _feats(feats), _feats(inducing)
         y, yv = _vec(y), _vec(yvar)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         indices = np.ascontiguousarray(indices, dtype=np.int64)
-        keep = (prog, x, u, y, yv, offsets, indices)
-        args = (self.ptr, prog, nops, _d(x), C.c_int64(x.shape[0]), C.c_int(x.shape[1]), _d(y),
-                _d(yv), _d(u), C.c_int64(u.shape[0]), _i(indices), _i(offsets),
-                C.c_int64(len(offsets) - 1), C.c_double(measurement_nugget),
-                C.c_double(inducing_nugget))
-        return args, keep, u.shape[0]
+        keep = (progs, x, u, y, yv, offsets, indices)
+        flat = tuple(v for pr in progs for v in pr)
+        args = (self.ptr,) + flat + (_d(x), C.c_int64(x.shape[0]), C.c_int(x.shape[1]), _d(y),
+                                     _d(yv), _d(u), C.c_int64(u.shape[0]), _i(indices), _i(offsets),
+                                     C.c_int64(len(offsets) - 1), C.c_double(measurement_nugget),
+                                     C.c_double(inducing_nugget))
+        return args, keep, u.shape[0], len(progs) == 3
 
     def sparse_fit(self, ops, params, feats, y, inducing, offsets, indices, yvar=None,
-                   measurement_nugget=1e-8, inducing_nugget=1e-8):
+                   measurement_nugget=1e-8, inducing_nugget=1e-8, fu=None, uu=None):
         """Returns (SparseFit, information[m], log_likelihood)."""
-        args, keep, m = self._sparse_args(ops, params, feats, y, yvar, inducing, offsets, indices,
-                                          measurement_nugget, inducing_nugget)
+        args, keep, m, three = self._sparse_args(ops, params, feats, y, yvar, inducing, offsets,
+                                                 indices, measurement_nugget, inducing_nugget, fu, uu)
         out = C.c_void_p()
         info = np.empty(m)
         ll = C.c_double()
-        _check(lib().ab_sparse_fit(*args, C.byref(out), _d(info), C.byref(ll)))
+        fn = lib().ab_sparse_fit2 if three else lib().ab_sparse_fit
+        _check(fn(*args, C.byref(out), _d(info), C.byref(ll)))
         del keep
         return SparseFit(self, out), info, ll.value
 
     def sparse_log_likelihood(self, ops, params, feats, y, inducing, offsets, indices, yvar=None,
-                              measurement_nugget=1e-8, inducing_nugget=1e-8):
-        args, keep, _ = self._sparse_args(ops, params, feats, y, yvar, inducing, offsets, indices,
-                                          measurement_nugget, inducing_nugget)
+                              measurement_nugget=1e-8, inducing_nugget=1e-8, fu=None, uu=None):
+        args, keep, _, three = self._sparse_args(ops, params, feats, y, yvar, inducing, offsets,
+                                                 indices, measurement_nugget, inducing_nugget, fu, uu)
         ll = C.c_double()
-        _check(lib().ab_sparse_log_likelihood(*args, C.byref(ll)))
+        fn = lib().ab_sparse_log_likelihood2 if three else lib().ab_sparse_log_likelihood
+        _check(fn(*args, C.byref(ll)))
         del keep
         return ll.value
 
@@ -589,15 +598,21 @@ class SparseFit:
         _check(lib().ab_sparse_info(self.ptr, None, C.byref(ll)))
         return ll.value
 
-    def predict(self, ops, params, test_feats, what):
+    def predict(self, ops, params, test_feats, what, prior=None):
+        """prior: optional (ops, params) of k(test, test) when it differs from the cross program."""
         prog, nops = program(ops, params)
         t = _feats(test_feats)
         p = t.shape[0]
         mean = np.empty(p)
         var = np.empty(p) if what == MARGINAL else None
         cov = np.empty((p, p), order="F") if what == JOINT else None
-        _check(lib().ab_sparse_predict(self.h.ptr, self.ptr, prog, nops, _d(t), C.c_int64(p),
-                                       C.c_int(what), _d(mean), _d(var), _d(cov)))
+        if prior is None:
+            _check(lib().ab_sparse_predict(self.h.ptr, self.ptr, prog, nops, _d(t), C.c_int64(p),
+                                           C.c_int(what), _d(mean), _d(var), _d(cov)))
+        else:
+            pprog, pnops = program(*prior)
+            _check(lib().ab_sparse_predict2(self.h.ptr, self.ptr, prog, nops, pprog, pnops, _d(t),
+                                            C.c_int64(p), C.c_int(what), _d(mean), _d(var), _d(cov)))
         return mean, var, cov
 
     def export_R(self):

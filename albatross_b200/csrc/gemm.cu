@@ -139,14 +139,15 @@ __device__ __forceinline__ void load_tile(double *smem, const double *g, int64_t
   }
 }
 
-// AB_GEMM_FASTLOAD (round-2 candidate, compile-checked only so far; tools/sweep.sh g_fast*): the k-loop
-// above spends 310 non-DMMA instructions per 64 DMMA, almost all of them the 64-bit address and
-// predicate arithmetic load_tile redoes for every k-tile (profiles/r01cdef_ncu_and_probe_summary.md).
+// AB_GEMM_FASTLOAD (default on; measured 8192^3 NN / TN / NT 30.9 / 32.7 / 31.0 -> 33.3 / 33.4 / 33.5
+// TFLOP/s, profiles/r02a_gemm_sweep.txt): the k-loop of load_tile spends 310 non-DMMA instructions per 64
+// DMMA, almost all of them the 64-bit address and predicate arithmetic it redoes for every k-tile
+// (profiles/r01cdef_ncu_and_probe_summary.md).
 // For CTA tiles that lie fully inside the operands (16-byte aligned, k a multiple of BK) everything but
 // the k offset is loop invariant: a thread keeps one source pointer and one shared-memory offset per
 // operand; chunk `it` of a k-tile is a fixed stride away from chunk 0 in both address spaces.
 #ifndef AB_GEMM_FASTLOAD
-#define AB_GEMM_FASTLOAD 0
+#define AB_GEMM_FASTLOAD 1
 #endif
 
 template <int EXT, bool KMAJOR> struct FastTile {
@@ -439,84 +440,6 @@ gemv_n_kernel(int64_t m, int64_t k, double alpha, const double *__restrict__ A, 
   }
 }
 
-// Wide-row variant (round-2 candidate, run-time switch AB_GEMV_WIDE=1, compile-checked only so far).
-// The kernel above reads 256-byte column segments 8 * lda bytes apart and reaches 0.9 TB/s
-// (profiles/r01_gemm_kernel_isolated.txt: 16384 x 16384 in 2.45 ms); the one-rhs triangular solves of
-// fit / log-likelihood are made of such products (66 ms of the 6.26 s bench step).  Here a CTA covers
-// 64 * WR rows with 16-byte loads (WR * 512 contiguous bytes per column), its WC = 8 / WR warp columns
-// take every WC-th column, eight independent loads in flight per thread, deterministic reduction.
-template <int WR>
-__global__ void __launch_bounds__(256)
-gemv_n_wide_kernel(int64_t m, int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
-                   const double *__restrict__ b, double beta, double *c) {
-  constexpr int WC = 8 / WR;
-  __shared__ double2 red[WC][WR * 32];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int wr = warp % WR;
-  const int wc = warp / WR;
-  const int64_t row = blockIdx.x * static_cast<int64_t>(64 * WR) + wr * 64 + 2 * lane;
-  double2 acc[4] = {{0., 0.}, {0., 0.}, {0., 0.}, {0., 0.}};
-  if (row + 1 < m) {
-    const double *a = A + row;
-    int64_t kk = wc;
-    for (; kk + 7 * WC < k; kk += 8 * WC) {
-      double2 v[8];
-      double s[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        v[u] = *reinterpret_cast<const double2 *>(a + (kk + u * WC) * lda);
-        s[u] = b[kk + u * WC];
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        acc[u & 3].x = fma(v[u].x, s[u], acc[u & 3].x);
-        acc[u & 3].y = fma(v[u].y, s[u], acc[u & 3].y);
-      }
-    }
-    for (; kk < k; kk += WC) {
-      const double2 v = *reinterpret_cast<const double2 *>(a + kk * lda);
-      acc[0].x = fma(v.x, b[kk], acc[0].x);
-      acc[0].y = fma(v.y, b[kk], acc[0].y);
-    }
-  } else if (row < m) { // last (odd) row of the matrix
-    const double *a = A + row;
-    for (int64_t kk = wc; kk < k; kk += WC) {
-      acc[0].x = fma(a[kk * lda], b[kk], acc[0].x);
-    }
-  }
-  red[wc][wr * 32 + lane] = make_double2((acc[0].x + acc[1].x) + (acc[2].x + acc[3].x),
-                                         (acc[0].y + acc[1].y) + (acc[2].y + acc[3].y));
-  __syncthreads();
-  if (wc == 0 && row < m) {
-    double2 total = make_double2(0., 0.);
-#pragma unroll
-    for (int w = 0; w < WC; ++w) {
-      total.x += red[w][wr * 32 + lane].x;
-      total.y += red[w][wr * 32 + lane].y;
-    }
-    double v0 = alpha * total.x, v1 = alpha * total.y;
-    if (beta != 0.) {
-      v0 = fma(beta, c[row], v0);
-    }
-    c[row] = v0;
-    if (row + 1 < m) {
-      if (beta != 0.) {
-        v1 = fma(beta, c[row + 1], v1);
-      }
-      c[row + 1] = v1;
-    }
-  }
-}
-
-static bool gemv_wide_enabled() {
-  static const bool on = []() {
-    const char *e = std::getenv("AB_GEMV_WIDE");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
 // c[m] = alpha * A^T b + beta * c ; A stored k x m (k contiguous).  One CTA per output element.
 __global__ void __launch_bounds__(256)
 gemv_t_kernel(int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
@@ -570,15 +493,6 @@ int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double
     if (ta) {
       gemv_t_kernel<<<static_cast<unsigned>(m), 256, 0, h->stream>>>(k, alpha, A.p, A.ld, B.p,
                                                                       beta, C.p);
-    } else if (gemv_wide_enabled() && m >= 128 * 96 && reinterpret_cast<uintptr_t>(A.p) % 16 == 0 &&
-               A.ld % 2 == 0) {
-      if (m >= 512 * 96) {
-        gemv_n_wide_kernel<8><<<static_cast<unsigned>((m + 511) / 512), 256, 0, h->stream>>>(
-            m, k, alpha, A.p, A.ld, B.p, beta, C.p);
-      } else {
-        gemv_n_wide_kernel<2><<<static_cast<unsigned>((m + 127) / 128), 256, 0, h->stream>>>(
-            m, k, alpha, A.p, A.ld, B.p, beta, C.p);
-      }
     } else {
       const unsigned blocks = static_cast<unsigned>((m + GEMV_ROWS - 1) / GEMV_ROWS);
       gemv_n_kernel<<<blocks, GEMV_ROWS * GEMV_WARPS, 0, h->stream>>>(m, k, alpha, A.p, A.ld, B.p,

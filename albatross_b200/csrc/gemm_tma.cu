@@ -5,8 +5,10 @@
 // i.e. the trailing DSYRK / DGEMM updates of the blocked Cholesky (reference: the GEMV inner loop of
 // third_party/eigen/Eigen/src/Cholesky/LDLT.h:349-355 that this library turns into level-3 work).
 //
-// ROUND-2 CANDIDATE: compile- and ptxas-checked only, not yet run on a GPU.  It is selected at run time
-// by AB_GEMM_TMA=1 (read once); without it gemm() never comes here.
+// Default path of every NT product large enough for one CTA tile (gemm() in gemm.cu falls back to the
+// cp.async kernel otherwise); AB_GEMM_TMA=0 (read once) switches it off, which the parity tests use to
+// compare the two kernels.  Measured on B200 (profiles/r02a_*): 8192^3 34.2 TFLOP/s vs 31.0 (cuBLAS 35.5),
+// 16384^2 x 1024 34.4 vs 30.3, factorisation N = 32 768 31.3 vs 28.2 TFLOP/s.
 //
 // Why: the cp.async kernel (gemm.cu) keeps the DMMA pipe 84 % busy; its k-loop spends 310 non-DMMA
 // instructions per 64 DMMA on per-thread address / predicate arithmetic and meets at a CTA-wide
@@ -288,7 +290,7 @@ bool make_map(CUtensorMap *map, const MatView &M, int64_t rows, int64_t kext) {
 bool gemm_tma_enabled() {
   static const bool on = []() {
     const char *e = std::getenv("AB_GEMM_TMA");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr || e[0] != '0';
   }();
   return on;
 }

@@ -34,8 +34,8 @@ struct DevOp {
   int kind;
   int flags;
   double a2, a1, b2, b1, amp;
-  double ab1, ab2; // amp * b1, amp * b2 (AB_GRAM_AMPFOLD: amplitude folded into the polynomial)
-  // AB_GRAM_SCALEDEXP: a2 * 2048/ln2, a1 * 2048/ln2, and the high word of the largest argument
+  double ab1, ab2; // amp * b1, amp * b2 (amplitude folded into the Matern polynomial)
+  // scaled-domain exp: a2 * 2048/ln2, a1 * 2048/ln2, and the high word of the largest argument
   // (d^2 resp. d) for which a * arg >= -708, rounded down (conservative)
   double a2s, a1s;
   int lim_hi;

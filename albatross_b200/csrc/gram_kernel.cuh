@@ -25,17 +25,10 @@
 namespace ab {
 
 constexpr int TILE = 64;
-// Mirror staging buffer, element (c, r) of the tile (column c, row r):
-//   swizzled (default): stage[c * 64 + 2 * ((r >> 1) ^ (c & 7)) + (r & 1)] — 16-byte granules
-//     XOR-swizzled by the column, so that both the producer (lane = row pair, one STS.128 per column)
-//     and the mirror (lane = column, one LDS.128 per row pair) are bank-conflict free;
-//   padded (AB_GRAM_SWIZZLE=0): stage[c * 65 + r], 8-byte accesses (producer 2-way conflicted).
-#ifndef AB_GRAM_SWIZZLE
-#define AB_GRAM_SWIZZLE 0
-#endif
-constexpr bool STAGE_SWIZZLE = AB_GRAM_SWIZZLE != 0;
-constexpr int LDT = STAGE_SWIZZLE ? TILE : TILE + 1;
-__device__ __forceinline__ int stage_granule(int c, int g) { return c * TILE + 2 * (g ^ (c & 7)); }
+// Mirror staging buffer, element (c, r) of the tile (column c, row r): stage[c * 65 + r], 8-byte
+// accesses (producer 2-way conflicted).  An XOR-swizzled layout with 16-byte accesses measured slower
+// (2.00 vs 1.95 ms, profiles/r01d_sweeps.txt) and was removed in round 2.
+constexpr int LDT = TILE + 1;
 constexpr int GRAM_THREADS = 256;
 // A thread owns 2 rows x COLS columns per pass (2 * COLS pairs in flight); 8 / COLS passes cover the
 // 64 columns of the tile.
@@ -44,76 +37,34 @@ constexpr int GRAM_THREADS = 256;
 // lean fp64 exp / sqrt
 // ------------------------------------------------------------------------------------------------
 
-// Instruction-count knobs of the fixed-evaluator kernels (the kernel is issue-bound: 82 warp
-// instructions per pair of which 35 FP64, profiles/r01c_*; tools/sweep.sh measures each):
-//   AB_GRAM_ONECHECK  one range check per pass (the exp arguments only; a zero / subnormal /
-//                     non-finite squared distance turns into a NaN argument) with a cold re-evaluation,
-//                     instead of a check-and-patch branch after the sqrt batch and after every exp batch
-//   AB_GRAM_PTRS      loop-carried pointers for the direct / mirror stores and the staging buffer
-//                     instead of 64-bit index arithmetic in every pass
-//   AB_GRAM_EXPMAD    2^n scaling of exp as shift + multiply-add (2 integer instructions, not 3)
+// What the fixed-evaluator kernels ship with (the kernel is issue-bound, not HBM-bound: a warp-wide DFMA
+// holds the FP64 pipe 2 cycles, 3 with three distinct sources; IMAD / LOP3 / SHF cost 1-2 cycles each
+// next to FP64 work, tools/issue_probe.cu).  Every choice was timed at N = 32 768, SE + Matern52, full
+// symmetric, after passing tests/test_gpu_gram.py on the same box (profiles/r02a_gram_sweep.txt):
+//   * one range check per pass (AB_GRAM_ONECHECK, default on; =0 keeps the round-1 check-and-patch
+//     branches for comparison): a zero / subnormal / non-finite squared distance or an out-of-range exp
+//     argument triggers a cold re-evaluation of the pass with the checked evaluator;
+//   * exp by range reduction in table steps straight from the distance: with as = a * 2048/ln2 (host
+//     side), t = fma(d, as, magic), r' = fma(d, as, -m) (one rounding, |r'| <= 1/2),
+//     exp = 2^(m/2048) (1 + r' (c1 + r' (c2 + r' c3))): 7 FP64 instructions per exp instead of 9.  Same
+//     error bound against the exact exp(a d) as a two-step reduction, 1.57 (1 + |x|) 2^-53 (CPU emulation,
+//     tools/exp_emulation.c), up to 2 |x| 2^-53 away from libm's exp(fl(a d));
+//   * 2^n scaling as shift + multiply-add; amplitude folded into the Matern polynomial coefficients;
+//   * interior-tile store addresses as 64-bit tile base + 32-bit element offset.
+// Together 1.956 -> 1.821 ms (4392 -> 4717 GB/s, 0.670 -> 0.720 of the measured HBM peak).  Measured and
+// removed in round 2: exp constants from constant memory (2.000 ms), expm1 as r * fma(r, p, 1) (1.954),
+// 2x2 / 4x4 micro-block tile order (1.997 / 2.122), 4 columns per pass at 1 CTA/SM (2.296), loop-carried
+// store pointers (2.17, round 1), XOR-swizzled staging (2.00, round 1).
 #ifndef AB_GRAM_ONECHECK
 #define AB_GRAM_ONECHECK 1
-#endif
-#ifndef AB_GRAM_PTRS
-#define AB_GRAM_PTRS 0
-#endif
-#ifndef AB_GRAM_EXPMAD
-#define AB_GRAM_EXPMAD 1
-#endif
-// Round-2 candidates (compile-checked only so far; tools/sweep.sh k_r2_*), all aimed at the cost table
-// of tools/issue_probe.cu — a DFMA with three distinct register sources costs 3 cycles instead of 2,
-// IMAD / LOP3 / SHF cost 1-2 each next to FP64 work:
-//   AB_GRAM_QFORM    expm1(r) as r * fma(r, p, 1) (two 2-source instructions) instead of fma(p, r*r, r)
-//   AB_GRAM_AMPFOLD  amplitude folded into the Matern polynomial coefficients (one FP64 less per term)
-//   AB_GRAM_OFF32    interior-tile store addresses as 64-bit tile base + 32-bit element offset
-//                    (one IMAD.WIDE per address) instead of 64-bit index arithmetic in every pass
-#ifndef AB_GRAM_QFORM
-#define AB_GRAM_QFORM 0
-#endif
-#ifndef AB_GRAM_AMPFOLD
-#define AB_GRAM_AMPFOLD 0
-#endif
-#ifndef AB_GRAM_OFF32
-#define AB_GRAM_OFF32 0
-#endif
-//   AB_GRAM_UCONST   the four exp constants whose low words are not zero come from constant memory (read
-//                    through uniform registers, loaded once) instead of being re-materialised with
-//                    IMAD.MOV / UMOV pairs in every pass (ptxas does that under the 128-register cap)
-#ifndef AB_GRAM_UCONST
-#define AB_GRAM_UCONST 0
-#endif
-//   AB_GRAM_SCALEDEXP  range reduction in table steps straight from the distance: with as = a * 2048/ln2
-//                    (host side), t = fma(d, as, magic), r' = fma(d, as, -m) (one rounding, |r'| <= 1/2),
-//                    exp = 2^(m/2048) (1 + r' (c1 + r' (c2 + r' c3))): 7 FP64 instructions per exp instead of
-//                    9 (no a * d product, one reduction step).  Same error bound against the exact
-//                    exp(a d) as the two-step reduction, 1.57 (1 + |x|) 2^-53 (CPU emulation, 2e7 samples),
-//                    but up to 2 |x| 2^-53 away from libm's exp(fl(a d)), i.e. from the reference's last bits.
-//                    The range check moves to the distance (unsigned high word against a host-side limit).
-#ifndef AB_GRAM_SCALEDEXP
-#define AB_GRAM_SCALEDEXP 0
 #endif
 
 // res * 2^(m >> SHIFT) for a normal result (no overflow: the argument range is checked)
 template <int SHIFT> __device__ __forceinline__ double exp_scale(double res, int m) {
-#if AB_GRAM_EXPMAD
   int hi;
   asm("mad.lo.s32 %0, %1, 1048576, %2;" : "=r"(hi) : "r"(m >> SHIFT), "r"(__double2hiint(res)));
   return __hiloint2double(hi, __double2loint(res));
-#else
-  return __hiloint2double(__double2hiint(res) + (m & ~((1 << SHIFT) - 1)) * (1 << (20 - SHIFT)),
-                          __double2loint(res));
-#endif
 }
-
-#if AB_GRAM_UCONST
-// {2048/ln2, -ln2/2048 high part, -ln2/2048 low part, 1/6}
-static __constant__ double EXP_BIG_K[4] = {2954.639443740597, -0x1.62e42fef00000p-12,
-                                           -0x1.473de6af278edp-45, 0.16666666666666666};
-#define AB_EXPK(i, literal) EXP_BIG_K[i]
-#else
-#define AB_EXPK(i, literal) (literal)
-#endif
 
 // exp(x) for -708 <= x <= -0 (the argument of every radial kernel): x = (128 n + j) ln2/128 + r,
 // exp(x) = 2^n T[j] (1 + r + ... + r^5/120), |r| <= ln2/256; 10 FP64-pipe instructions, <= 1 ulp.
@@ -142,18 +93,14 @@ __device__ __forceinline__ double exp_core(double x, const double *__restrict__ 
 // <= 1.3 ulp (tools/make_exp_table.py generates both tables).
 __device__ __forceinline__ double exp_core_big(double x, const double *__restrict__ tab,
                                                int &hi_max) {
-  const double t = fma(x, AB_EXPK(0, 2954.639443740597), 6755399441055744.0); // x * 2048/ln2
+  const double t = fma(x, 2954.639443740597, 6755399441055744.0); // x * 2048/ln2
   const int m = __double2loint(t);
   const double mf = t - 6755399441055744.0;
-  double r = fma(mf, AB_EXPK(1, -0x1.62e42fef00000p-12), x);
-  r = fma(mf, AB_EXPK(2, -0x1.473de6af278edp-45), r);
-  const double p = fma(r, AB_EXPK(3, 0.16666666666666666), 0.5);
-#if AB_GRAM_QFORM
-  const double q = r * fma(r, p, 1.); // expm1(r)
-#else
+  double r = fma(mf, -0x1.62e42fef00000p-12, x);
+  r = fma(mf, -0x1.473de6af278edp-45, r);
+  const double p = fma(r, 0.16666666666666666, 0.5);
   const double r2 = r * r;
   const double q = fma(p, r2, r); // expm1(r)
-#endif
   const double tj = tab[m & 2047];
   const double res = fma(tj, q, tj);
   hi_max = max(hi_max, __double2hiint(x));
@@ -194,7 +141,7 @@ __device__ __forceinline__ double exp_patch(double x, double fast) {
   return (x < -708.0) ? 0. : ((x != x) ? x : fast);
 }
 
-// AB_GRAM_SCALEDEXP: exp(a d) from d and as = a * 2048/ln2, for 0 <= d <= 708 / |a| (checked by the caller).
+// exp(a d) from d and as = a * 2048/ln2, for 0 <= d <= 708 / |a| (checked by the caller).
 static __constant__ double EXP_SCALED_C[3] = {0x1.62e42fefa39efp-12,                       // ln2/2048
                                               0x1.62e42fefa39efp-12 * 0x1.62e42fefa39efp-12 * 0.5,
                                               0x1.62e42fefa39efp-12 * 0x1.62e42fefa39efp-12 *
@@ -457,8 +404,7 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
     }
   } else {
     double v[NP], e[NP];
-#if AB_GRAM_SCALEDEXP
-    static_assert(TAB == TAB_2048, "AB_GRAM_SCALEDEXP uses the 2048-entry table");
+    static_assert(TAB == TAB_2048, "the scaled-domain exp uses the 2048-entry table");
     {
       const double as = KIND == LS_SE ? o.a2s : o.a1s;
       const unsigned lim = static_cast<unsigned>(o.lim_hi);
@@ -480,28 +426,7 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
         hi_acc = max(hi_acc, worst > lim ? 0x7fffffff : EXP_HI_LIMIT);
       }
     }
-#else
-    if constexpr (KIND == LS_SE) {
-      const double a2 = o.a2;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        v[i] = a2 * d2[i];
-      }
-    } else {
-      const double a1 = o.a1;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        v[i] = a1 * dist[i];
-      }
-    }
-    if constexpr (CHECK) {
-      exp_batch<NP, TAB>(v, tab, e);
-    } else {
-      exp_batch_nocheck<NP, TAB>(v, tab, e, hi_acc);
-    }
-#endif
     const double amp = o.amp;
-#if AB_GRAM_AMPFOLD
     if constexpr (KIND == LS_M32 || KIND == LS_M52) {
       // amp * (1 + b1 d [+ b2 d^2]) * e as fma(poly', e, out), poly' = amp + (amp b1) d [+ (amp b2) d^2]
       const double ab1 = o.ab1, ab2 = o.ab2;
@@ -515,7 +440,6 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
       }
       return;
     }
-#endif
     if constexpr (KIND == LS_M32) {
       const double b1 = o.b1;
 #pragma unroll
@@ -545,12 +469,7 @@ __device__ __forceinline__ void fixed_term(const DevOp &o, const double (&d2)[NP
 #define AB_GRAM_TABLE 1
 #endif
 constexpr int FIXED_TABLE = AB_GRAM_TABLE;
-#ifdef AB_GRAM_TABLE_GLOBAL
-constexpr bool TABLE_IN_SMEM = false;
-static_assert(AB_GRAM_TABLE != 2, "the replicated table lives in shared memory");
-#else
 constexpr bool TABLE_IN_SMEM = true;
-#endif
 
 template <int K0, int K1, int K2, int TAB = FIXED_TABLE> struct EvalFixed {
   static constexpr bool NEED_EQ = K0 == LS_NOISE || K1 == LS_NOISE || K2 == LS_NOISE;
@@ -624,50 +543,8 @@ template <int K0, int K1, int K2, int TAB = FIXED_TABLE> struct EvalFixed {
 #endif
 constexpr unsigned SB = AB_GRAM_SB;
 
-// AB_GRAM_MICRO (round-2 candidate; tools/sweep.sh k_r2_micro builds gram.cu and gram_fixed.cu with it):
-// a CTA takes the MB x MB tiles of a micro-block one after the other, rows fastest — for MB = 2: (2I, 2J),
-// (2I+1, 2J), (2I, 2J+1), (2I+1, 2J+1) — so that its consecutive direct tiles extend the same 64 columns
-// (and its mirror tiles the same 64 columns of the upper triangle) by the next 512 bytes: the store
-// pattern of a 128 x 128 (MB = 4: 256 x 256) tile (pure-store probe: 5223 / 5440 vs 4993 GB/s,
-// profiles/r01c_store_pattern.txt) and 1/MB of the 2 MB pages per byte written, with the 64 x 64 kernel
-// body unchanged.  Work item t = MB^2 * micro-block + sub-tile; micro-blocks are walked in the
-// super-block order below at 1/MB resolution.
-#ifndef AB_GRAM_MICRO
-#define AB_GRAM_MICRO 0 // 0 = off; 2 or 4 = micro-block edge MB in tiles (MB * MB work items per micro-block)
-#endif
-static_assert(AB_GRAM_MICRO == 0 || AB_GRAM_MICRO == 2 || AB_GRAM_MICRO == 4, "micro-block edge");
-constexpr unsigned MICRO_MB = AB_GRAM_MICRO == 0 ? 1u : static_cast<unsigned>(AB_GRAM_MICRO);
-constexpr unsigned MICRO_ITEMS = MICRO_MB * MICRO_MB;
-template <bool SYM> constexpr bool micro_blocks() { return SYM && AB_GRAM_MICRO != 0; }
-
-// First work item of a CTA and the one after t (grid of G CTAs).
-template <bool SYM> __device__ __forceinline__ unsigned first_item(unsigned cta) {
-  return micro_blocks<SYM>() ? MICRO_ITEMS * cta : cta;
-}
-template <bool SYM> __device__ __forceinline__ unsigned advance_item(unsigned t, unsigned G) {
-  if (micro_blocks<SYM>()) {
-    return (t % MICRO_ITEMS) != MICRO_ITEMS - 1u ? t + 1u : t + MICRO_ITEMS * G - (MICRO_ITEMS - 1u);
-  }
-  return t + G;
-}
-
 template <bool SYM>
 __device__ __forceinline__ bool decode_tile(unsigned t, unsigned tiles_i, unsigned &I, unsigned &J) {
-  if (micro_blocks<SYM>()) {
-    const unsigned micro = t / MICRO_ITEMS, sub = t % MICRO_ITEMS;
-    const unsigned sb = micro / (SB * SB);
-    const unsigned local = micro % (SB * SB);
-    unsigned i = static_cast<unsigned>((sqrtf(8.f * static_cast<float>(sb) + 1.f) - 1.f) * 0.5f);
-    while (i * (i + 1u) / 2u > sb) {
-      --i;
-    }
-    while ((i + 1u) * (i + 2u) / 2u <= sb) {
-      ++i;
-    }
-    I = MICRO_MB * (i * SB + local % SB) + sub % MICRO_MB;
-    J = MICRO_MB * ((sb - i * (i + 1u) / 2u) * SB + local / SB) + sub / MICRO_MB;
-    return I < tiles_i && J <= I;
-  }
   if (SYM) {
     const unsigned sb = t / (SB * SB);
     const unsigned local = t % (SB * SB);
@@ -692,7 +569,7 @@ template <bool SYM>
 __device__ __forceinline__ unsigned next_tile(unsigned t, unsigned step, unsigned nitems,
                                               unsigned tiles_i, unsigned &I, unsigned &J) {
   while (t < nitems && !decode_tile<SYM>(t, tiles_i, I, J)) {
-    t = advance_item<SYM>(t, step);
+    t += step;
   }
   return t;
 }
@@ -702,22 +579,13 @@ inline int64_t gram_items(bool sym, int64_t tiles_i, int64_t tiles_j) {
   if (!sym) {
     return tiles_i * tiles_j;
   }
-  if (AB_GRAM_MICRO != 0) { // micro-blocks of MB x MB tiles, MB^2 work items each
-    const int64_t mt = (tiles_i + MICRO_MB - 1) / MICRO_MB;
-    const int64_t nsb = (mt + SB - 1) / SB;
-    return nsb * (nsb + 1) / 2 * SB * SB * MICRO_ITEMS;
-  }
   const int64_t nsb = (tiles_i + SB - 1) / SB;
   return nsb * (nsb + 1) / 2 * SB * SB;
 }
 
-// Interior-tile stores.  AB_GRAM_STREAM_STORES (tools/sweep.sh) marks them evict-first.
+// Interior-tile stores (evict-first marking measured no gain, profiles/r01d_sweeps.txt).
 template <class T> __device__ __forceinline__ void gram_store(T *dst, const T &v) {
-#ifdef AB_GRAM_STREAM_STORES
-  __stcs(dst, v);
-#else
   *dst = v;
-#endif
 }
 
 constexpr int FEAT_SLOTS = 2; // TILE * AB_MAX_DIM / GRAM_THREADS feature elements per thread
@@ -757,34 +625,9 @@ __device__ __forceinline__ void mirror_slice(const double *__restrict__ stage,
                                              unsigned I, unsigned J, bool interior, int part,
                                              int lane, int warp) {
   constexpr int KS = 8 / PARTS;
-  static_assert(!STAGE_SWIZZLE || KS % 2 == 0, "a mirror slice is a whole number of row pairs");
   const int64_t i0 = static_cast<int64_t>(I) * TILE;
   const int64_t j0 = static_cast<int64_t>(J) * TILE;
   const int rbase = warp * 8 + part * KS;
-  if (STAGE_SWIZZLE) {
-#pragma unroll
-    for (int k = 0; k < KS; k += 2) {
-      const int r = rbase + k;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int c = lane + 32 * half;
-        const double2 v = *reinterpret_cast<const double2 *>(stage + stage_granule(c, r >> 1));
-        double *dst = out + (j0 + c) + (i0 + r) * ld;
-        if (interior) {
-          gram_store(dst, v.x);
-          gram_store(dst + ld, v.y);
-        } else if (j0 + c < n) {
-          if (i0 + r < n) {
-            dst[0] = v.x;
-          }
-          if (i0 + r + 1 < n) {
-            dst[ld] = v.y;
-          }
-        }
-      }
-    }
-    return;
-  }
   if (interior) {
     double *dst = out + (j0 + lane) + (i0 + rbase) * ld;
     const double *src = stage + lane * LDT + rbase;
@@ -813,20 +656,6 @@ __device__ __forceinline__ void mirror_slice(const double *__restrict__ stage,
   }
 }
 
-// The same slice of an interior tile through loop-carried pointers (AB_GRAM_PTRS, padded layout):
-// dst = &out[j0 + lane, i0 + rbase], src = &stage[lane][rbase].
-template <int PARTS>
-__device__ __forceinline__ void mirror_slice_ptr(double *__restrict__ dst,
-                                                 const double *__restrict__ src, int64_t ld) {
-  constexpr int KS = 8 / PARTS;
-#pragma unroll
-  for (int k = 0; k < KS; ++k) {
-    gram_store(dst, src[k]);
-    gram_store(dst + 32, src[32 * LDT + k]);
-    dst += ld;
-  }
-}
-
 // Hides the provenance of a pointer from the optimiser.
 __device__ __forceinline__ double *opaque_ptr(double *p) {
   unsigned long long v = reinterpret_cast<unsigned long long>(p);
@@ -836,8 +665,8 @@ __device__ __forceinline__ double *opaque_ptr(double *p) {
   return q;
 }
 
-// The same slice of an interior tile addressed as tile base + 32-bit element offset (AB_GRAM_OFF32,
-// padded layout): mbase = &out[j0, i0]; one IMAD.WIDE per address instead of 64-bit index arithmetic.
+// The same slice of an interior tile addressed as tile base + 32-bit element offset: mbase = &out[j0, i0];
+// one IMAD.WIDE per address instead of 64-bit index arithmetic.
 template <int PARTS>
 __device__ __forceinline__ void mirror_slice_off(const double *__restrict__ stage,
                                                  double *__restrict__ mbase, unsigned ld32, int part,
@@ -888,7 +717,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   const double *tab = TABLE_IN_SMEM ? EV::lane_table(gram_smem, lane) : EV::table();
   const bool need_dist = DIM != 1 && EV::need_dist(P);
 
-  unsigned t = first_item<SYM>(blockIdx.x);
+  unsigned t = blockIdx.x;
   unsigned I = 0, J = 0;
   double px[FEAT_SLOTS], py[FEAT_SLOTS];
   t = next_tile<SYM>(t, gridDim.x, ntiles, static_cast<unsigned>(tiles_i), I, J);
@@ -898,15 +727,11 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
   // pending mirror of the previous tile: bit 0 = pending, bit 1 = interior, bit 2 = staging buffer
   unsigned pend = 0, pI = 0, pJ = 0;
   unsigned buf = 0;
-  constexpr bool USE_OFF32 = AB_GRAM_OFF32 != 0;
-  static_assert(!(USE_OFF32 && STAGE_SWIZZLE), "AB_GRAM_OFF32 is written for the padded staging layout");
-  static_assert(!(USE_OFF32 && AB_GRAM_PTRS != 0), "AB_GRAM_OFF32 and AB_GRAM_PTRS are alternatives");
+  // interior-tile stores are addressed as 64-bit tile base + 32-bit element offset (one IMAD.WIDE per
+  // address instead of 64-bit index arithmetic in every pass: -18 instructions per pass, measured
+  // 1.956 -> 1.913 ms, profiles/r02a_gram_sweep.txt)
   const unsigned ld32 = static_cast<unsigned>(ld);
-  double *mbase = out; // &out[j0, i0] of the pending mirror (AB_GRAM_OFF32)
-  constexpr bool USE_PTRS = AB_GRAM_PTRS != 0;
-  static_assert(!(USE_PTRS && STAGE_SWIZZLE), "AB_GRAM_PTRS is written for the padded staging layout");
-  double *mptr = out;             // next slice of the pending mirror (interior tiles, AB_GRAM_PTRS)
-  const double *msrc = stage0;
+  double *mbase = out; // &out[j0, i0] of the pending mirror
 
   while (t < ntiles) {
     const unsigned cI = I, cJ = J;
@@ -915,7 +740,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
     const bool mirror = SYM && cI != cJ && !(flags & AB_GRAM_LOWER_ONLY);
     // interior tile of a 16-byte aligned output: no bounds checks anywhere below
     const bool interior = (i0 + TILE <= n) && (j0 + TILE <= m) && !(flags & GRAM_UNALIGNED) &&
-                          (!USE_OFF32 || (ld >> 24) == 0); // 64 * ld elements fit a 32-bit offset
+                          (ld >> 24) == 0; // 64 * ld elements fit a 32-bit offset
     double *stage = stage0 + buf * STAGE;
 
     // every reader of xs / ys of the previous tile is done, every slice of the mirror before the
@@ -932,8 +757,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
     __syncthreads();
 
     // prefetch the next tile's features; they are consumed at the top of the next iteration
-    t = next_tile<SYM>(advance_item<SYM>(t, gridDim.x), gridDim.x, ntiles,
-                       static_cast<unsigned>(tiles_i), I, J);
+    t = next_tile<SYM>(t + gridDim.x, gridDim.x, ntiles, static_cast<unsigned>(tiles_i), I, J);
     if (t < ntiles) {
       fetch_features<DIM>(fx, ldfx, n, fy, ldfy, m, I, J, tid, px, py);
     }
@@ -947,14 +771,8 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
       }
     }
     const int64_t gi = i0 + r0;
-    double *tbase = out + i0 + j0 * ld; // AB_GRAM_OFF32: &out[i0, j0]
-    if (USE_OFF32) {
-      tbase = opaque_ptr(tbase); // keep base + 32-bit offset (else ptxas re-derives 64-bit indices)
-    }
-    // AB_GRAM_PTRS: loop-carried pointers (pass p handles columns p * 8 COLS + warp * COLS + k)
-    double *dptr = out + gi + (j0 + warp * COLS) * ld; // direct store, column k = 0
-    const double *yp = ys + warp * COLS * DIM;         // y features of column k = 0
-    double *sp = stage + warp * COLS * LDT + r0;       // staging element (column k = 0, row r0)
+    // &out[i0, j0]; opaque: keeps base + 32-bit offset (else ptxas re-derives 64-bit indices)
+    double *tbase = opaque_ptr(out + i0 + j0 * ld);
 
 #pragma unroll 1
     for (int pass = 0; pass < PASSES; ++pass) {
@@ -967,7 +785,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
         double yj[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
-          yj[d] = USE_PTRS ? yp[k * DIM + d] : ys[c * DIM + d];
+          yj[d] = ys[c * DIM + d];
         }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -1027,21 +845,11 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
 
       // direct tile: rows i0 + r0 (+1), columns j0 + c; 16-byte stores, 512 contiguous bytes/warp
       if (interior) {
-        if (USE_OFF32) {
-          unsigned off = static_cast<unsigned>(r0) + static_cast<unsigned>(cbase) * ld32;
+        unsigned off = static_cast<unsigned>(r0) + static_cast<unsigned>(cbase) * ld32;
 #pragma unroll
-          for (int k = 0; k < COLS; ++k) {
-            gram_store(reinterpret_cast<double2 *>(tbase + off),
-                       make_double2(vals[2 * k], vals[2 * k + 1]));
-            off += ld32;
-          }
-        } else {
-          double *dst = USE_PTRS ? dptr : out + gi + (j0 + cbase) * ld;
-#pragma unroll
-          for (int k = 0; k < COLS; ++k) {
-            gram_store(reinterpret_cast<double2 *>(dst), make_double2(vals[2 * k], vals[2 * k + 1]));
-            dst += ld;
-          }
+        for (int k = 0; k < COLS; ++k) {
+          gram_store(reinterpret_cast<double2 *>(tbase + off), make_double2(vals[2 * k], vals[2 * k + 1]));
+          off += ld32;
         }
       } else {
         const bool unaligned = flags & GRAM_UNALIGNED;
@@ -1065,34 +873,17 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
 #pragma unroll
         for (int k = 0; k < COLS; ++k) {
           const int c = cbase + k;
-          if (STAGE_SWIZZLE) {
-            *reinterpret_cast<double2 *>(stage + stage_granule(c, lane)) =
-                make_double2(vals[2 * k], vals[2 * k + 1]);
-          } else if (USE_PTRS) {
-            sp[k * LDT] = vals[2 * k];
-            sp[k * LDT + 1] = vals[2 * k + 1];
-          } else {
-            stage[c * LDT + r0] = vals[2 * k];
-            stage[c * LDT + r0 + 1] = vals[2 * k + 1];
-          }
+          stage[c * LDT + r0] = vals[2 * k];
+          stage[c * LDT + r0 + 1] = vals[2 * k + 1];
         }
       }
       if (SYM && (pend & 1u)) {
-        if (USE_PTRS && (pend & 2u)) {
-          mirror_slice_ptr<PASSES>(mptr, msrc, ld);
-          mptr += (8 / PASSES) * ld;
-          msrc += 8 / PASSES;
-        } else if (USE_OFF32 && (pend & 2u)) {
+        if (pend & 2u) {
           mirror_slice_off<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, mbase, ld32, pass, lane, warp);
         } else {
           mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
                                pass, lane, warp);
         }
-      }
-      if (USE_PTRS) {
-        dptr += static_cast<int64_t>(8 * COLS) * ld;
-        yp += 8 * COLS * DIM;
-        sp += 8 * COLS * LDT;
       }
     }
 
@@ -1100,13 +891,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
       pend = mirror ? (1u | (interior ? 2u : 0u) | (buf << 2)) : 0u;
       pI = cI;
       pJ = cJ;
-      if (USE_OFF32) {
-        mbase = opaque_ptr(out + j0 + i0 * ld);
-      }
-      if (USE_PTRS) { // slice 0 of the pending mirror: rows j0 + lane (+32), columns i0 + warp * 8 ...
-        mptr = out + (j0 + lane) + (i0 + warp * 8) * ld;
-        msrc = stage + lane * LDT + warp * 8;
-      }
+      mbase = opaque_ptr(out + j0 + i0 * ld);
       if (mirror) {
         buf ^= 1u;
       }
@@ -1117,11 +902,7 @@ gram_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, in
     __syncthreads();
 #pragma unroll 1
     for (int part = 0; part < PASSES; ++part) {
-      if (USE_PTRS && (pend & 2u)) {
-        mirror_slice_ptr<PASSES>(mptr, msrc, ld);
-        mptr += (8 / PASSES) * ld;
-        msrc += 8 / PASSES;
-      } else if (USE_OFF32 && (pend & 2u)) {
+      if (pend & 2u) {
         mirror_slice_off<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, mbase, ld32, part, lane, warp);
       } else {
         mirror_slice<PASSES>(stage0 + ((pend >> 2) & 1u) * STAGE, out, ld, n, pI, pJ, pend & 2u,
@@ -1160,8 +941,7 @@ inline cudaError_t gram_launch(ab_handle_s *h, const DevProg &P, const double *f
     configured = true;
   }
   const int64_t resident = static_cast<int64_t>(MINB) * h->sm_count;
-  const int64_t units = micro_blocks<SYM>() ? ntiles / MICRO_ITEMS : ntiles; // what a CTA strides over
-  const unsigned grid = static_cast<unsigned>(units < resident ? units : resident);
+  const unsigned grid = static_cast<unsigned>(ntiles < resident ? ntiles : resident);
   gram_kernel<DIM, SYM, EV, COLS, MINB><<<grid, GRAM_THREADS, smem, h->stream>>>(
       P, fx, ldfx, n, fy, ldfy, m, out, ld, tiles_i, ntiles, flags);
   return cudaGetLastError();

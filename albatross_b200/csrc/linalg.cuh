@@ -28,8 +28,8 @@ enum GemmFlags : unsigned {
 int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double alpha, MatView A,
          MatView B, double beta, MatView C);
 
-// TMA-fed variant of the C = alpha A B^T + beta C product (gemm_tma.cu; round-2 candidate, selected by
-// AB_GEMM_TMA=1).  AB_ERR_UNSUPPORTED = shape / alignment it does not cover: use the cp.async kernel.
+// TMA-fed kernel of the C = alpha A B^T + beta C product (gemm_tma.cu; on unless AB_GEMM_TMA=0).
+// AB_ERR_UNSUPPORTED = shape / alignment it does not cover: use the cp.async kernel.
 bool gemm_tma_enabled();
 int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, double alpha, MatView A,
                 MatView B, double beta, MatView C);

@@ -209,7 +209,17 @@ int cholqr_pass(ab_handle_s *h, Scope &sc, MatView C, int64_t rows, int64_t m, a
                 double *d_g, double *d_yy) {
   ab_matrix_s *S = nullptr;
   AB_TRY(matrix_new(h, m + 1, m + 1, &S));
-  int s = gemm(h, GEMM_TRANS_A | GEMM_LOWER, m + 1, m + 1, rows, 1., C, C, 0., view(S));
+  // GEMM_LOWER writes only the lower triangle: the strict upper triangle and the ld padding are
+  // recycled pool memory and must not ride through the all-reduce (or stay in the stored factors)
+  int s = AB_OK;
+  if (cudaMemsetAsync(S->d, 0, static_cast<size_t>(S->ld) * (m + 1) * sizeof(double), h->stream) !=
+      cudaSuccess) {
+    set_error("cholqr memset failed");
+    s = AB_ERR_CUDA;
+  }
+  if (s == AB_OK) {
+    s = gemm(h, GEMM_TRANS_A | GEMM_LOWER, m + 1, m + 1, rows, 1., C, C, 0., view(S));
+  }
   if (s == AB_OK) {
     s = dist_allreduce_sum(h, S->d, S->ld * (m + 1));
   }
@@ -235,7 +245,10 @@ int cholqr_pass(ab_handle_s *h, Scope &sc, MatView C, int64_t rows, int64_t m, a
   return factorize(h, S, L);
 }
 
-int sparse_fit_impl(ab_handle_s *h, const DevProg &P, const double *feats, int64_t n, int dim,
+// P_ff: k(Measurement, Measurement) for the diagonal blocks of K_ff, P_fu: k(Measurement, U), P_uu:
+// k(U, U) (sparse_gp.hpp:646-679); the three differ when the tree holds a MeasurementOnly term.
+int sparse_fit_impl(ab_handle_s *h, const DevProg &P_ff, const DevProg &P_fu, const DevProg &P_uu,
+                    const double *feats, int64_t n, int dim,
                     const double *y, const double *yvar, const double *inducing, int64_t m,
                     const int64_t *indices, const int64_t *offsets, int64_t ngroups,
                     double measurement_nugget, double inducing_nugget, ab_sparse_fit_s *fit) {
@@ -309,13 +322,14 @@ int sparse_fit_impl(ab_handle_s *h, const DevProg &P, const double *feats, int64
   // ---- K_uu = L_u L_u^T (sparse_gp.hpp:673-679) -----------------------------------------------
   phase_begin(h, PH_GRAM);
   ab_matrix_s *Kuu = nullptr;
-  AB_TRY(gram_sym_device(h, P, fit->u, AB_GRAM_LOWER_ONLY, &Kuu));
+  AB_TRY(gram_sym_device(h, P_uu, fit->u, AB_GRAM_LOWER_ONLY, &Kuu));
   add_diag_scalar_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, h->stream>>>(
       Kuu->d, Kuu->ld, m, inducing_nugget);
   AB_LAUNCHED(h);
   // ---- K_fu straight into the top block of C (sparse_gp.hpp:670-671) ---------------------------
   if (n > 0) {
-    int s = gram_into(h, P, dim, false, XF->d, XF->ld, n, fit->u->d, fit->u->ld, m, C->d, C->ld, 0u);
+    int s = gram_into(h, P_fu, dim, false, XF->d, XF->ld, n, fit->u->d, fit->u->ld, m, C->d, C->ld,
+                      0u);
     if (s != AB_OK) {
       matrix_delete(h, Kuu);
       return s;
@@ -348,7 +362,7 @@ int sparse_fit_impl(ab_handle_s *h, const DevProg &P, const double *feats, int64
     AB_TRY(sc.alloc(nb, &d_kd));
     AB_TRY(sc.alloc(nb, &d_scale));
     AB_TRY(sc.alloc(nb * static_cast<size_t>(nchunks), &d_part));
-    AB_TRY(gram_diag_into(h, P, dim, XF->d, XF->ld, n, static_cast<double *>(d_kd)));
+    AB_TRY(gram_diag_into(h, P_ff, dim, XF->d, XF->ld, n, static_cast<double *>(d_kd)));
     row_sumsq_partial_kernel<<<grid2(n, nchunks), 256, 0, h->stream>>>(
         C->d, C->ld, n, m, static_cast<double *>(d_part));
     AB_LAUNCHED(h);
@@ -374,7 +388,7 @@ int sparse_fit_impl(ab_handle_s *h, const DevProg &P, const double *feats, int64
         continue;
       }
       const MatView Cg = Cv.sub(o, 0);
-      AB_TRY(gram_into(h, P, dim, true, XF->d + o * dim, XF->ld, sz, nullptr, 0, 0, A->d, A->ld,
+      AB_TRY(gram_into(h, P_ff, dim, true, XF->d + o * dim, XF->ld, sz, nullptr, 0, 0, A->d, A->ld,
                        AB_GRAM_LOWER_ONLY));
       AB_TRY(add_diag(h, view(A), sz, static_cast<double *>(d_var) + o));
       AB_TRY(gemm(h, GEMM_TRANS_B | GEMM_LOWER, sz, sz, m, -1., Cg, Cg, 1., view(A)));
@@ -387,8 +401,11 @@ int sparse_fit_impl(ab_handle_s *h, const DevProg &P, const double *feats, int64
     }
   }
   AB_TRY(download_bytes(h, h->d_flags, sizeof(int), h->h_flags));
-  if (h->h_flags[0] != INT_MAX) {
-    set_error("a block of A = K_ff - Q_ff + noise is not positive definite");
+  // every rank must take the same sequence of collectives: agree on failure before the first one
+  const bool local_bad = h->h_flags[0] != INT_MAX;
+  if (dist_total(h, local_bad ? 1 : 0) > 0) {
+    set_error(local_bad ? "a block of A = K_ff - Q_ff + noise is not positive definite"
+                        : "a block of A = K_ff - Q_ff + noise is not positive definite on another rank");
     return AB_ERR_NOT_PD;
   }
 
@@ -439,23 +456,26 @@ using namespace ab;
 
 extern "C" {
 
-int ab_sparse_fit(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
-                  const double *y, const double *yvar, const double *inducing, int64_t m,
-                  const int64_t *indices, const int64_t *offsets, int64_t ngroups,
-                  double measurement_nugget, double inducing_nugget, ab_sparse *out,
-                  double *information, double *log_likelihood) {
+int ab_sparse_fit2(ab_handle h, const ab_op *prog_ff, int nops_ff, const ab_op *prog_fu, int nops_fu,
+                   const ab_op *prog_uu, int nops_uu, const double *feats, int64_t n, int dim,
+                   const double *y, const double *yvar, const double *inducing, int64_t m,
+                   const int64_t *indices, const int64_t *offsets, int64_t ngroups,
+                   double measurement_nugget, double inducing_nugget, ab_sparse *out,
+                   double *information, double *log_likelihood) {
   AB_REQUIRE(h != nullptr && out != nullptr && n >= 0 && m >= 1 && ngroups >= 0, "null / sizes");
   AB_REQUIRE(inducing != nullptr && offsets != nullptr && (n == 0 || (feats && y && indices)),
              "null inputs");
   AB_REQUIRE(offsets[0] == 0 && offsets[ngroups] == n, "group offsets must cover all observations");
   AB_REQUIRE(dim >= 1 && dim <= AB_MAX_DIM, "feature dimension");
   Lock lock(h);
-  DevProg P;
-  AB_TRY(compile_program(prog, nops, &P));
+  DevProg P_ff, P_fu, P_uu;
+  AB_TRY(compile_program(prog_ff, nops_ff, &P_ff));
+  AB_TRY(compile_program(prog_fu, nops_fu, &P_fu));
+  AB_TRY(compile_program(prog_uu, nops_uu, &P_uu));
   timings_reset(h);
   auto *fit = new ab_sparse_fit_s();
-  int s = sparse_fit_impl(h, P, feats, n, dim, y, yvar, inducing, m, indices, offsets, ngroups,
-                          measurement_nugget, inducing_nugget, fit);
+  int s = sparse_fit_impl(h, P_ff, P_fu, P_uu, feats, n, dim, y, yvar, inducing, m, indices, offsets,
+                          ngroups, measurement_nugget, inducing_nugget, fit);
   cudaEventRecord(h->ev_total_end, h->stream);
   if (s != AB_OK) {
     cudaStreamSynchronize(h->stream);
@@ -471,6 +491,16 @@ int ab_sparse_fit(ab_handle h, const ab_op *prog, int nops, const double *feats,
   }
   *out = fit;
   return s;
+}
+
+int ab_sparse_fit(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n, int dim,
+                  const double *y, const double *yvar, const double *inducing, int64_t m,
+                  const int64_t *indices, const int64_t *offsets, int64_t ngroups,
+                  double measurement_nugget, double inducing_nugget, ab_sparse *out,
+                  double *information, double *log_likelihood) {
+  return ab_sparse_fit2(h, prog, nops, prog, nops, prog, nops, feats, n, dim, y, yvar, inducing, m,
+                        indices, offsets, ngroups, measurement_nugget, inducing_nugget, out,
+                        information, log_likelihood);
 }
 
 int ab_sparse_free(ab_handle h, ab_sparse f) {
@@ -503,9 +533,23 @@ int ab_sparse_log_likelihood(ab_handle h, const ab_op *prog, int nops, const dou
   return ab_sparse_free(h, f);
 }
 
-int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
-                      const double *test_feats, int64_t p, int what, double *mean, double *var,
-                      double *cov) {
+int ab_sparse_log_likelihood2(ab_handle h, const ab_op *prog_ff, int nops_ff, const ab_op *prog_fu,
+                              int nops_fu, const ab_op *prog_uu, int nops_uu, const double *feats,
+                              int64_t n, int dim, const double *y, const double *yvar,
+                              const double *inducing, int64_t m, const int64_t *indices,
+                              const int64_t *offsets, int64_t ngroups, double measurement_nugget,
+                              double inducing_nugget, double *log_likelihood) {
+  AB_REQUIRE(log_likelihood != nullptr, "null");
+  ab_sparse f = nullptr;
+  AB_TRY(ab_sparse_fit2(h, prog_ff, nops_ff, prog_fu, nops_fu, prog_uu, nops_uu, feats, n, dim, y,
+                        yvar, inducing, m, indices, offsets, ngroups, measurement_nugget,
+                        inducing_nugget, &f, nullptr, log_likelihood));
+  return ab_sparse_free(h, f);
+}
+
+int ab_sparse_predict2(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
+                       const ab_op *prior_prog, int prior_nops, const double *test_feats, int64_t p,
+                       int what, double *mean, double *var, double *cov) {
   AB_REQUIRE(h != nullptr && f != nullptr && p >= 0 && (p == 0 || (test_feats && mean)), "null");
   AB_REQUIRE(what == AB_PREDICT_MEAN || (what == AB_PREDICT_MARGINAL && var != nullptr) ||
                  (what == AB_PREDICT_JOINT && cov != nullptr),
@@ -514,8 +558,9 @@ int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
     return AB_OK;
   }
   Lock lock(h);
-  DevProg P;
+  DevProg P, PP; // cross k(u, test) and prior k(test, test) (sparse_gp.hpp:470, 491-495, 516)
   AB_TRY(compile_program(prog, nops, &P));
+  AB_TRY(compile_program(prior_prog, prior_nops, &PP));
   Scope sc(h);
   timings_reset(h);
   const int64_t m = f->m;
@@ -548,7 +593,7 @@ int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
       AB_TRY(sc.alloc(pb, &d_prior));
       AB_TRY(sc.alloc(pb, &d_q));
       AB_TRY(sc.alloc(pb, &d_s));
-      AB_TRY(gram_diag_device(h, P, T, static_cast<double *>(d_prior)));
+      AB_TRY(gram_diag_device(h, PP, T, static_cast<double *>(d_prior)));
       AB_TRY(column_dots(h, view(cross), view(cross), m, p, static_cast<double *>(d_q)));
       AB_TRY(column_dots(h, view(S), view(S), m, p, static_cast<double *>(d_s)));
       phase_end(h, PH_PREDICT);
@@ -561,7 +606,7 @@ int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
       }
     } else {
       ab_matrix_s *prior = nullptr;
-      AB_TRY(gram_sym_device(h, P, T, AB_GRAM_FULL, &prior));
+      AB_TRY(gram_sym_device(h, PP, T, AB_GRAM_FULL, &prior));
       sc.own(prior);
       AB_TRY(gemm(h, GEMM_TRANS_A, p, p, m, -1., view(cross), view(cross), 1., view(prior)));
       AB_TRY(gemm(h, GEMM_TRANS_A, p, p, m, 1., view(S), view(S), 1., view(prior)));
@@ -573,6 +618,12 @@ int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
   }
   cudaEventRecord(h->ev_total_end, h->stream);
   return download(h, mu, 0, 0, p, 1, mean);
+}
+
+int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
+                      const double *test_feats, int64_t p, int what, double *mean, double *var,
+                      double *cov) {
+  return ab_sparse_predict2(h, f, prog, nops, prog, nops, test_feats, p, what, mean, var, cov);
 }
 
 int ab_sparse_export_R(ab_handle h, ab_sparse f, double *R) {

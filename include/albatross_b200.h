@@ -305,6 +305,21 @@ AB_API int ab_sparse_fit(ab_handle h, const ab_op *prog, int nops, const double 
                   const int64_t *indices, const int64_t *offsets, int64_t ngroups,
                   double measurement_nugget, double inducing_nugget, ab_sparse *out,
                   double *information, double *log_likelihood);
+/*
+ * ab_sparse_fit with the three covariance programs the reference evaluates (sparse_gp.hpp:646-679):
+ *   prog_ff  k(Measurement<X>, Measurement<X>)  diagonal blocks of K_ff (:657)
+ *   prog_fu  k(Measurement<X>, U)               K_fu (:670-671)
+ *   prog_uu  k(U, U)                            K_uu (:673-674)
+ * They differ when the tree holds a MeasurementOnly term (src/covariance_functions/measurement.hpp:
+ * 70-114), the configuration of the reference's own sparse tests
+ * (tests/lib/albatross/test/test_models.h:26-30).  ab_sparse_fit passes one program three times.
+ */
+AB_API int ab_sparse_fit2(ab_handle h, const ab_op *prog_ff, int nops_ff, const ab_op *prog_fu,
+                   int nops_fu, const ab_op *prog_uu, int nops_uu, const double *feats, int64_t n,
+                   int dim, const double *y, const double *yvar, const double *inducing, int64_t m,
+                   const int64_t *indices, const int64_t *offsets, int64_t ngroups,
+                   double measurement_nugget, double inducing_nugget, ab_sparse *out,
+                   double *information, double *log_likelihood);
 AB_API int ab_sparse_free(ab_handle h, ab_sparse f);
 AB_API int ab_sparse_info(ab_sparse f, int64_t *m, double *log_likelihood);
 /* model.log_likelihood(dataset) for the sparse model (:539-603): a fresh fit, only the scalar kept. */
@@ -313,10 +328,21 @@ AB_API int ab_sparse_log_likelihood(ab_handle h, const ab_op *prog, int nops, co
                              const double *inducing, int64_t m, const int64_t *indices,
                              const int64_t *offsets, int64_t ngroups, double measurement_nugget,
                              double inducing_nugget, double *log_likelihood);
+AB_API int ab_sparse_log_likelihood2(ab_handle h, const ab_op *prog_ff, int nops_ff, const ab_op *prog_fu,
+                              int nops_fu, const ab_op *prog_uu, int nops_uu, const double *feats,
+                              int64_t n, int dim, const double *y, const double *yvar,
+                              const double *inducing, int64_t m, const int64_t *indices,
+                              const int64_t *offsets, int64_t ngroups, double measurement_nugget,
+                              double inducing_nugget, double *log_likelihood);
 /* _predict_impl x3 sparse_gp.hpp:468-536; outputs as ab_gp_predict. */
 AB_API int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
                       const double *test_feats, int64_t p, int what, double *mean, double *var,
                       double *cov);
+/* ab_sparse_predict with separate programs for the cross covariance k(U, X*) (:470, :483, :509) and
+ * the prior k(X*, X*) (:491-495, :516). */
+AB_API int ab_sparse_predict2(ab_handle h, ab_sparse f, const ab_op *cross_prog, int cross_nops,
+                       const ab_op *prior_prog, int prior_nops, const double *test_feats, int64_t p,
+                       int what, double *mean, double *var, double *cov);
 /* sigma_R (m x m upper triangular, column-major, get_R linalg/qr_utils.hpp:18-27) with P = I. */
 AB_API int ab_sparse_export_R(ab_handle h, ab_sparse f, double *R);
 

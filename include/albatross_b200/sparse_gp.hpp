@@ -173,15 +173,11 @@ private:
                    double *log_likelihood) const {
     using M = Measurement<FeatureType>;
     // K_ff blocks are k(Measurement, Measurement), K_fu is k(Measurement, U), K_uu is k(U, U)
-    // (sparse_gp.hpp:646-679).  The device call takes one program: they must flatten identically.
+    // (sparse_gp.hpp:646-679): three programs, which differ when the tree holds a MeasurementOnly term
+    // (the reference's standard sparse configuration, tests/lib/albatross/test/test_models.h:26-30).
     const Program p_ff = this->covariance_function_.template program<M, M>();
     const Program p_fu = this->covariance_function_.template program<M, U>();
     const Program p_uu = this->covariance_function_.template program<U, U>();
-    if (!same_program(p_ff, p_fu) || !same_program(p_ff, p_uu)) {
-      check_status(AB_ERR_UNSUPPORTED,
-                   "sparse GP: covariance differs between measurements and inducing points "
-                   "(measurement-only term); no device form yet");
-    }
     const auto indexer = build_indexer(independent_group_function_, features);
     const GroupCSR csr = to_csr(indexer);
     const PackedFeatures f = pack_features(features);
@@ -192,15 +188,17 @@ private:
     const double *yvar = targets.has_covariance() ? targets.covariance.diagonal().data() : nullptr;
     const ab_handle h = this->device()->get();
     if (fit_out != nullptr) {
-      ALBATROSS_B200_CHECK(ab_sparse_fit(h, p_ff.data(), static_cast<int>(p_ff.size()), f.data.data(), f.n,
-                                         f.dim, y.data(), yvar, fu.data.data(), fu.n, csr.indices.data(),
-                                         csr.offsets.data(), csr.ngroups(), measurement_nugget_.value,
-                                         inducing_nugget_.value, fit_out, information, log_likelihood));
+      ALBATROSS_B200_CHECK(ab_sparse_fit2(
+          h, p_ff.data(), static_cast<int>(p_ff.size()), p_fu.data(), static_cast<int>(p_fu.size()), p_uu.data(),
+          static_cast<int>(p_uu.size()), f.data.data(), f.n, f.dim, y.data(), yvar, fu.data.data(), fu.n,
+          csr.indices.data(), csr.offsets.data(), csr.ngroups(), measurement_nugget_.value,
+          inducing_nugget_.value, fit_out, information, log_likelihood));
     } else {
-      ALBATROSS_B200_CHECK(ab_sparse_log_likelihood(
-          h, p_ff.data(), static_cast<int>(p_ff.size()), f.data.data(), f.n, f.dim, y.data(), yvar,
-          fu.data.data(), fu.n, csr.indices.data(), csr.offsets.data(), csr.ngroups(),
-          measurement_nugget_.value, inducing_nugget_.value, log_likelihood));
+      ALBATROSS_B200_CHECK(ab_sparse_log_likelihood2(
+          h, p_ff.data(), static_cast<int>(p_ff.size()), p_fu.data(), static_cast<int>(p_fu.size()), p_uu.data(),
+          static_cast<int>(p_uu.size()), f.data.data(), f.n, f.dim, y.data(), yvar, fu.data.data(), fu.n,
+          csr.indices.data(), csr.offsets.data(), csr.ngroups(), measurement_nugget_.value,
+          inducing_nugget_.value, log_likelihood));
     }
   }
 
@@ -209,19 +207,11 @@ private:
                            int what, double *mean, double *var, double *cov) const {
     const Program cross = this->covariance_function_.template program<U, FeatureType>();
     const Program prior = this->covariance_function_.template program<FeatureType, FeatureType>();
-    if (!same_program(cross, prior)) {
-      check_status(AB_ERR_UNSUPPORTED, "sparse GP predict: cross and prior covariance programs differ");
-    }
     const PackedFeatures test = pack_features(features);
-    ALBATROSS_B200_CHECK(ab_sparse_predict(fit.device_fit->dev->get(), fit.device_fit->f, cross.data(),
-                                           static_cast<int>(cross.size()), test.data.data(), test.n, what,
-                                           mean, var, cov));
-  }
-
-  static bool same_program(const Program &a, const Program &b) {
-    return a.size() == b.size() && std::equal(a.begin(), a.end(), b.begin(), [](const ab_op &x, const ab_op &y) {
-             return x.op == y.op && x.p0 == y.p0 && x.p1 == y.p1;
-           });
+    ALBATROSS_B200_CHECK(ab_sparse_predict2(fit.device_fit->dev->get(), fit.device_fit->f, cross.data(),
+                                            static_cast<int>(cross.size()), prior.data(),
+                                            static_cast<int>(prior.size()), test.data.data(), test.n, what, mean,
+                                            var, cov));
   }
 
   Parameter measurement_nugget_;

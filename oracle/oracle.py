@@ -83,6 +83,16 @@ def menu_program(cov_id, p):
     raise ValueError(cov_id)
 
 
+def menu_program_plain(cov_id, p):
+    """Program of menu entry ``cov_id`` when at least one side is NOT a Measurement<> (K_fu, K_uu and
+    the predictions of the sparse GP; cross / prior of the exact GP): MeasurementOnly terms vanish
+    (measurement.hpp:70-114).  Only entry 10 differs from menu_program."""
+    if cov_id == 10:
+        p = list(map(float, p))
+        return [SE], [p[0], p[1]]
+    return menu_program(cov_id, p)
+
+
 class Ref:
     """The compiled reference.  ``Ref.available()`` is False when the .so was not built/shipped."""
 
@@ -567,8 +577,13 @@ class Restate:
 
     @classmethod
     def sparse_gp(cls, ops, params, feats, y, inducing, keys_per_item, test=None, what=-1,
-                  yvar=None, measurement_nugget=1e-8, inducing_nugget=1e-8, want_ll=False):
+                  yvar=None, measurement_nugget=1e-8, inducing_nugget=1e-8, want_ll=False,
+                  fu=None, uu=None):
+        """fu / uu: optional (ops, params) of the K_fu and K_uu (= prediction) programs when they
+        differ from the K_ff one (MeasurementOnly terms, sparse_gp.hpp:646-679)."""
         prog, nops = _prog(ops, params)
+        prog_fu, nops_fu = _prog(*fu) if fu is not None else (prog, nops)
+        prog_uu, nops_uu = _prog(*uu) if uu is not None else (prog, nops)
         x = np.ascontiguousarray(feats, dtype=np.float64).ravel()
         n = len(x)
         u = np.ascontiguousarray(inducing, dtype=np.float64)
@@ -586,12 +601,12 @@ class Restate:
         if what == 2:
             out["cov"] = np.empty((pn, pn), order="F")
         ll = C.c_double()
-        cls.lib().rs_sparse_gp(prog, nops, _d(x), C.c_int64(n), _d(y), _d(yv), _d(u), C.c_int64(m),
-                               _i(indices), _i(offsets), C.c_int64(len(offsets) - 1),
-                               C.c_double(measurement_nugget), C.c_double(inducing_nugget), _d(t),
-                               C.c_int64(pn), C.c_int(what), _d(out["information"]),
-                               _d(out.get("mean")), _d(out.get("var")), _d(out.get("cov")),
-                               C.byref(ll) if want_ll else None)
+        cls.lib().rs_sparse_gp2(prog, nops, prog_fu, nops_fu, prog_uu, nops_uu, _d(x), C.c_int64(n),
+                                _d(y), _d(yv), _d(u), C.c_int64(m), _i(indices), _i(offsets),
+                                C.c_int64(len(offsets) - 1), C.c_double(measurement_nugget),
+                                C.c_double(inducing_nugget), _d(t), C.c_int64(pn), C.c_int(what),
+                                _d(out["information"]), _d(out.get("mean")), _d(out.get("var")),
+                                _d(out.get("cov")), C.byref(ll) if want_ll else None)
         if want_ll:
             out["ll"] = ll.value
         return out

@@ -789,6 +789,23 @@ int rs_sparse_gp(const rs_op *prog, int nops, const double *feats, int64_t n, co
                  const int64_t *offsets, int64_t ngroups, double measurement_nugget,
                  double inducing_nugget, const double *test, int64_t p, int what,
                  double *information, double *mean, double *var, double *cov, double *ll) {
+  return rs_sparse_gp2(prog, nops, prog, nops, prog, nops, feats, n, y, yvar, inducing, m, indices,
+                       offsets, ngroups, measurement_nugget, inducing_nugget, test, p, what,
+                       information, mean, var, cov, ll);
+}
+
+/*
+ * The same with the three programs the reference evaluates (sparse_gp.hpp:646-679): prog = k(Measurement,
+ * Measurement) for the K_ff blocks, prog_fu = k(Measurement, U) for K_fu, prog_uu = k(U, U) for K_uu and for
+ * the predictions' cross / prior covariances (inducing and test features are both unwrapped there,
+ * :470-536).  They differ when the tree holds a MeasurementOnly term (measurement.hpp:70-114).
+ */
+int rs_sparse_gp2(const rs_op *prog, int nops, const rs_op *prog_fu, int nops_fu, const rs_op *prog_uu,
+                  int nops_uu, const double *feats, int64_t n, const double *y, const double *yvar,
+                  const double *inducing, int64_t m, const int64_t *indices, const int64_t *offsets,
+                  int64_t ngroups, double measurement_nugget, double inducing_nugget,
+                  const double *test, int64_t p, int what, double *information, double *mean,
+                  double *var, double *cov, double *ll) {
   const int dim = 1;
   /* reorder by group (:649-668) */
   double *xf = (double *)malloc((size_t)n * sizeof(double));
@@ -803,10 +820,10 @@ int rs_sparse_gp(const rs_op *prog, int nops, const double *feats, int64_t n, co
   }
   /* K_fu (:670-671), K_uu + nugget (:673-679) */
   double *K_fu = (double *)malloc((size_t)n * (size_t)m * sizeof(double));
-  rs_gram_cross(prog, nops, xf, n, inducing, m, dim, K_fu);
+  rs_gram_cross(prog_fu, nops_fu, xf, n, inducing, m, dim, K_fu);
   double *Kuu = (double *)malloc((size_t)m * (size_t)m * sizeof(double));
   int64_t *tru = (int64_t *)malloc((size_t)m * sizeof(int64_t));
-  rs_gram_sym(prog, nops, inducing, m, dim, Kuu);
+  rs_gram_sym(prog_uu, nops_uu, inducing, m, dim, Kuu);
   for (int64_t i = 0; i < m; ++i) {
     Kuu[IDX(i, i, m)] += inducing_nugget;
   }
@@ -926,7 +943,7 @@ int rs_sparse_gp(const rs_op *prog, int nops, const double *feats, int64_t n, co
   }
   if (what >= 0) {
     double *cross = (double *)malloc((size_t)m * (size_t)p * sizeof(double));
-    rs_gram_cross(prog, nops, inducing, m, test, p, dim, cross);
+    rs_gram_cross(prog_uu, nops_uu, inducing, m, test, p, dim, cross);
     for (int64_t j = 0; j < p; ++j) {
       double s = 0.;
       for (int64_t i = 0; i < m; ++i) {
@@ -944,7 +961,7 @@ int rs_sparse_gp(const rs_op *prog, int nops, const double *feats, int64_t n, co
         upper_T_solve(B, rows, m, S + (size_t)j * (size_t)m);
       }
       if (what == 1) {
-        rs_gram_diag(prog, nops, test, p, dim, var);
+        rs_gram_diag(prog_uu, nops_uu, test, p, dim, var);
         for (int64_t j = 0; j < p; ++j) {
           double q = 0., s = 0.;
           for (int64_t i = 0; i < m; ++i) {
@@ -954,7 +971,7 @@ int rs_sparse_gp(const rs_op *prog, int nops, const double *feats, int64_t n, co
           var[j] = var[j] - q + s;
         }
       } else {
-        rs_gram_sym(prog, nops, test, p, dim, cov);
+        rs_gram_sym(prog_uu, nops_uu, test, p, dim, cov);
         for (int64_t b = 0; b < p; ++b) {
           for (int64_t a = 0; a < p; ++a) {
             double q = 0., s = 0.;

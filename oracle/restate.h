@@ -82,6 +82,13 @@ int rs_sparse_gp(const rs_op *prog, int nops, const double *feats, int64_t n, co
                  double inducing_nugget, const double *test, int64_t p, int what,
                  double *information, double *mean, double *var, double *cov, double *ll);
 
+int rs_sparse_gp2(const rs_op *prog, int nops, const rs_op *prog_fu, int nops_fu, const rs_op *prog_uu,
+                  int nops_uu, const double *feats, int64_t n, const double *y, const double *yvar,
+                  const double *inducing, int64_t m, const int64_t *indices, const int64_t *offsets,
+                  int64_t ngroups, double measurement_nugget, double inducing_nugget,
+                  const double *test, int64_t p, int what, double *information, double *mean,
+                  double *var, double *cov, double *ll);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,9 +7,8 @@ them: the reference's LDLT needs 6.4 h and 96 GiB at N = 65 536).  Everything go
               pieces, and the value the 1-GPU recursion and the 2-GPU block-cyclic factorisation agreed on
               to 3e-13 (profiles/r01_bench_n65536.json, profiles/r01_bench_2gpu_n65536.json).
   configs[3]  LOO / leave-one-group-out CV, N = 32 768 (bench_loo_cv shape): the closed forms of
-              evaluation/cross_validation_utils.hpp:132-286 checked through independent solves.  Written
-              when the round-1 GPU budget was already spent: runs only with AB_RUN_UNVERIFIED=1 until its
-              first green run on a B200 (tools/gpu_r2_visit1.sh sets it).
+              evaluation/cross_validation_utils.hpp:132-286 checked through independent solves (first
+              green run on a B200: profiles/r02a_pytest.log).
 """
 import os
 
@@ -87,8 +86,6 @@ def test_exact_gp_config3_full_size(handle):
     assert abs(nll - (-64227.1208743)) <= RTOL * 64227.0, nll
 
 
-@pytest.mark.skipif(os.environ.get("AB_RUN_UNVERIFIED") != "1",
-                    reason="not yet run on a GPU (round-1 budget spent); enabled by tools/gpu_r2_visit1.sh")
 def test_loo_cv_config4_full_size(handle):
     n = 32768
     handle.trim()

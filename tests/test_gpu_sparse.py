@@ -9,7 +9,7 @@ import pytest
 
 from albatross_b200 import capi
 from albatross_b200.capi import JOINT, MARGINAL, MEAN
-from oracle.oracle import Restate, group_keys
+from oracle.oracle import Restate, group_keys, menu_program, menu_program_plain
 from tests.helpers import assert_close, features, prog, rel_err, targets
 
 pytestmark = pytest.mark.gpu
@@ -146,3 +146,74 @@ def test_sparse_large_fitc_consistency(handle):
     assert np.all(var > 0.0)
     f1.free()
     f2.free()
+
+
+# ---- covariances with a MeasurementOnly term: the reference's standard sparse configuration --------
+# (tests/lib/albatross/test/test_models.h:26-30; K_ff / K_fu / K_uu programs differ, sparse_gp.hpp:646-679)
+
+P10 = [1.0, 1.0, 0.1]
+
+
+def fit_mo(handle, params, x, y, u, keys, **kw):
+    ops, pp = menu_program(10, params)          # k(Measurement, Measurement): SE + noise
+    plain = menu_program_plain(10, params)      # any other pairing: SE alone
+    _, offsets, indices = capi.group_indexers(keys)
+    return handle.sparse_fit(ops, pp, x, y, u, offsets, indices, fu=plain, uu=plain, **kw), plain
+
+
+def test_sparse_measurement_only_fixture(handle, golden):
+    """Menu entry 10 (SE + measurement_only(IndependentNoise)) against the compiled reference."""
+    _, ref = golden
+    x, y, u, t = ref["spmo_x"], ref["spmo_y"], ref["spmo_u"], ref["spmo_test"]
+    for tag, gk, ga in (("fitc", 0, 0.0), ("pitc", 2, 2.0)):
+        for vtag, yv in (("", None), ("_yvar", ref["spmo_yvar"])):
+            (f, info, ll), plain = fit_mo(handle, P10, x, y, u, group_keys(x, gk, ga), yvar=yv)
+            mean, var, _ = f.predict(*plain, t, MARGINAL)
+            _, _, cov = f.predict(*plain, t, JOINT)
+            k = f"spmo_{tag}{vtag}"
+            assert_close(mean, ref[f"{k}_mean"], 1e-9, f"{k} mean")
+            scale = np.max(np.abs(ref[f"{k}_cov"]))
+            assert np.max(np.abs(var - ref[f"{k}_var"])) <= 1e-9 * scale, k
+            assert np.max(np.abs(cov - ref[f"{k}_cov"])) <= 1e-9 * scale, k
+            want = float(ref[f"{k}_ll"])
+            assert abs(ll - want) <= 1e-9 * abs(want), (k, ll, want)
+            f.free()
+
+
+def test_sparse_reference_test_model(handle, golden):
+    """MakeSparseGaussianProcess (test_models.h:44-57): SE(100, 100) + measurement_only(noise 0.1) on
+    make_toy_linear_data(), 25 uniformly spaced inducing points for 10 observations.  K_uu has condition
+    number ~1e12 relative to its 1e-8 nugget: means and the log-likelihood agree with the pivoted reference
+    to 1e-6 / 1e-7 here (the reference's own tolerance for this model against the dense GP is 1e-2 .. 1e-6,
+    tests/test_sparse_gp.cc:107-122,158-163)."""
+    _, ref = golden
+    x, y, u, t = ref["sptoy_x"], ref["sptoy_y"], ref["sptoy_u"], ref["sptoy_test"]
+    (f, info, ll), plain = fit_mo(handle, [100.0, 100.0, 0.1], x, y, u, np.arange(len(x)))
+    mean, var, _ = f.predict(*plain, t, MARGINAL)
+    err_mean = rel_err(mean, ref["sptoy_mean"])
+    err_var = float(np.max(np.abs(var - ref["sptoy_var"])))
+    err_ll = abs(ll - float(ref["sptoy_ll"])) / abs(float(ref["sptoy_ll"]))
+    print(f"sparse toy model: mean {err_mean:.2e} var(abs) {err_var:.2e} ll {err_ll:.2e}")
+    assert err_mean <= 1e-6 and err_var <= 1e-6 and err_ll <= 1e-6, (err_mean, err_var, err_ll)
+    f.free()
+
+
+@pytest.mark.parametrize("n,m,gk,ga", [(500, 40, 0, 0.0), (1500, 96, 2, 1.0)])
+def test_sparse_measurement_only_vs_oracle(handle, n, m, gk, ga):
+    x = features(n, 1, 3 * n).ravel()
+    y = targets(x)
+    u = Restate.linspace(x.min(), x.max(), m)
+    t = np.linspace(0.1, 9.9, 23)
+    keys = group_keys(x, gk, ga)
+    ops, pp = menu_program(10, P10)
+    plain = menu_program_plain(10, P10)
+    want = Restate.sparse_gp(ops, pp, x, y, u, keys, test=t, what=2, want_ll=True, fu=plain, uu=plain)
+    (f, info, ll), _ = fit_mo(handle, P10, x, y, u, keys)
+    mean, _, cov = f.predict(*plain, t, JOINT)
+    assert_close(mean, want["mean"], 1e-9, "mean")
+    assert abs(ll - want["ll"]) <= 1e-9 * abs(want["ll"]), (ll, want["ll"])
+    assert np.max(np.abs(cov - want["cov"])) <= 1e-9 * np.max(np.abs(want["cov"]))
+    _, offsets, indices = capi.group_indexers(keys)
+    assert_close(handle.sparse_log_likelihood(ops, pp, x, y, u, offsets, indices, fu=plain, uu=plain),
+                 ll, 1e-12)
+    f.free()

@@ -31,7 +31,7 @@ nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > $OUT/${TAG}
 leg 300 pytest bash -c "AB_RUN_UNVERIFIED=1 python -m pytest tests -m gpu -q --durations=5 2>&1 | tail -30 | tee $OUT/${TAG}_pytest.log"
 leg 60 issue_probe bash -c "tools/issue_probe 2>&1 | tee $OUT/${TAG}_issue_probe.txt | tail -8"
 leg 60 store_pattern bash -c "tools/store_pattern 32768 2>&1 | tee $OUT/${TAG}_store_pattern.txt | grep micro"
-leg 420 configs bash -c "python tools/bench_configs.py ${TAG} 2>&1 | tail -12 | cut -c1-1500"
+leg 600 configs bash -c "python tools/bench_configs.py ${TAG} 2>&1 | tail -12 | cut -c1-1500"
 leg 400 sweep_gram env SWEEP_ONLY='k_*' SWEEP_TEST="tests/test_gpu_gram.py" bash tools/sweep.sh run ${TAG}_gram
 leg 400 sweep_gemm env SWEEP_ONLY='g_*' bash tools/sweep.sh run ${TAG}_gemm
 leg 200 sweep_potrf env SWEEP_ONLY='p_*' bash tools/sweep.sh run ${TAG}_potrf

@@ -11,26 +11,13 @@ OUT=tools/sweep
 # tag : source : defines
 VARIANTS=(
   "k_base:gram_fixed:"
-  "k_r2_off32:gram_fixed:-DAB_GRAM_OFF32=1"
-  "k_r2_qform:gram_fixed:-DAB_GRAM_QFORM=1"
-  "k_r2_ampfold:gram_fixed:-DAB_GRAM_AMPFOLD=1"
-  "k_r2_uconst:gram_fixed:-DAB_GRAM_UCONST=1"
-  "k_r2_all:gram_fixed:-DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1"
-  "k_r2_all_but_off32:gram_fixed:-DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1"
-  "k_r2_scaledexp:gram_fixed:-DAB_GRAM_SCALEDEXP=1"
-  "k_r2_all_scaledexp:gram_fixed:-DAB_GRAM_SCALEDEXP=1 -DAB_GRAM_OFF32=1 -DAB_GRAM_AMPFOLD=1"
-  "k_r2_micro2:gram_fixed,gram:-DAB_GRAM_MICRO=2"
-  "k_r2_micro4:gram_fixed,gram:-DAB_GRAM_MICRO=4"
-  "k_r2_all_micro:gram_fixed,gram:-DAB_GRAM_MICRO=2 -DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1"
-  "k_r2_all_cols4_mb1:gram_fixed:-DAB_GRAM_OFF32=1 -DAB_GRAM_QFORM=1 -DAB_GRAM_AMPFOLD=1 -DAB_GRAM_UCONST=1 -DAB_GRAM_COLS=4 -DAB_GRAM_MINB=1"
-  "k_r1_nocheck:gram_fixed:-DAB_GRAM_ONECHECK=0 -DAB_GRAM_EXPMAD=0"
+  "k_r1_nocheck:gram_fixed:-DAB_GRAM_ONECHECK=0"
   "p_nb2048:linalg:"
   "p_nb1024:linalg:-DAB_POTRF_NB=1024"
   "p_nb4096:linalg:-DAB_POTRF_NB=4096"
-  "g_128x64x16s3c2:gemm:"
-  "g_fast:gemm:-DAB_GEMM_FASTLOAD=1"
-  "g_fast_s4:gemm:-DAB_GEMM_FASTLOAD=1 -DAB_GEMM_STAGES=4"
-  "g_128x128x16s3:gemm:-DAB_GEMM_BN=128 -DAB_GEMM_WARPS_M=2 -DAB_GEMM_WARPS_N=4 -DAB_GEMM_MIN_CTAS=1"
+  "g_base:gemm:"
+  "g_nofast:gemm:-DAB_GEMM_FASTLOAD=0"
+  "g_fast_s4:gemm:-DAB_GEMM_STAGES=4"
 )
 SKIP_RUN="${SWEEP_SKIP:-}"
 if [ "${1:-build}" = "build" ]; then
@@ -70,18 +57,13 @@ for v in "${VARIANTS[@]}"; do
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | tee -a $LOG
     if [ "$tag" = "p_nb2048" ]; then
-      # wide-row GEMV candidate (run-time switch): parity of the solve paths, then the solve_ms column
-      AB_GEMV_WIDE=1 timeout 200 python -m pytest tests/test_gpu_gp.py -m gpu -q -x 2>&1 | tail -2 | sed 's/^/gemv_wide: /' | tee -a $LOG
-      AB_GEMV_WIDE=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | sed 's/^/gemv_wide: /' | tee -a $LOG
       AB_POTRF_RECURSIVE=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 65536 2 2>&1 | sed 's/^/recursive: /' | tee -a $LOG
     fi
   elif [ "$src" = "gemm" ]; then
-    if [ "$tag" = "g_128x64x16s3c2" ]; then
-      # the TMA + mbarrier variant of the NT product (gemm_tma.cu) is a run-time switch of the same build;
-      # first parity (under a short timeout: a pipeline bug would hang), then timing
-      AB_GEMM_TMA=1 timeout 120 python -m pytest tests/test_gpu_gemm.py -m gpu -q -x 2>&1 | tail -3 | sed 's/^/tma: /' | tee -a $LOG
-      AB_GEMM_TMA=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 120 python tools/gemm_bench.py 8 2>&1 | sed 's/^/tma: /' | tee -a $LOG
-      AB_GEMM_TMA=1 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 120 python tools/potrf_bench.py 32768 2>&1 | sed 's/^/tma: /' | tee -a $LOG
+    if [ "$tag" = "g_base" ]; then
+      # the cp.async kernel alone (the TMA kernel of the NT product is on by default)
+      AB_GEMM_TMA=0 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 120 python tools/gemm_bench.py 8 2>&1 | sed 's/^/no-tma: /' | tee -a $LOG
+      AB_GEMM_TMA=0 ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 120 python tools/potrf_bench.py 32768 2>&1 | sed 's/^/no-tma: /' | tee -a $LOG
     fi
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/gemm_bench.py 8 2>&1 | tee -a $LOG
     ALBATROSS_B200_LIB=$PWD/$OUT/lib_$tag.so timeout 300 python tools/potrf_bench.py 32768 2>&1 | tee -a $LOG
