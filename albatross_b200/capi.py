@@ -74,7 +74,8 @@ SYMBOLS = [
     "ab_group_indexers", "ab_gemm", "ab_gp_cv_shard", "ab_gp_cv_scores", "ab_gp_predict2",
     "ab_sparse_fit", "ab_sparse_free", "ab_sparse_info", "ab_sparse_log_likelihood",
     "ab_sparse_predict", "ab_sparse_export_R", "ab_sparse_fit2", "ab_sparse_log_likelihood2",
-    "ab_sparse_predict2",
+    "ab_sparse_predict2", "ab_factor_sqrt_product", "ab_factor_sqrt_transpose_solve",
+    "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
     "ab_dist_factor_free", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
     "ab_partition_triangular",
@@ -227,6 +228,22 @@ class Factor:
 
     def sqrt_solve(self, rhs):
         return self._solve(lib().ab_factor_sqrt_solve, rhs)
+
+    def sqrt_product(self, rhs):
+        return self._solve(lib().ab_factor_sqrt_product, rhs)
+
+    def sqrt_transpose_solve(self, rhs):
+        return self._solve(lib().ab_factor_sqrt_transpose_solve, rhs)
+
+    def sqrt_transpose(self):
+        out = np.empty((self.n, self.n), order="F")
+        _check(lib().ab_factor_sqrt_transpose(self.h.ptr, self.ptr, _d(out)))
+        return out
+
+    def diagonal_sqrt(self):
+        out = np.empty(self.n)
+        _check(lib().ab_factor_diagonal_sqrt(self.h.ptr, self.ptr, _d(out)))
+        return out
 
     def log_determinant(self):
         out = C.c_double()

@@ -594,25 +594,48 @@ int ab_dist_gp_cv(ab_handle h, ab_factor factor, const double *y, const double *
   timings_reset(h);
   const int64_t n = factor->n;
   double local_score = 0.;
-  AB_TRY(gp_cv_impl(h, factor, y, information, indices, offsets, ngroups, what, h->rank, h->world,
-                    mean, var, nullptr, score != nullptr ? &local_score : nullptr, nullptr));
-  if (h->world > 1 && n > 0) {
+  // a rank-local failure (a held-out block that is not positive definite, an allocation) must not skip
+  // the assembling all-reduce: the other ranks would wait in NCCL for ever.  The status travels with
+  // the payload and every rank returns the agreed result after the same sequence of collectives.
+  const int local_status =
+      gp_cv_impl(h, factor, y, information, indices, offsets, ngroups, what, h->rank, h->world, mean,
+                 var, nullptr, score != nullptr ? &local_score : nullptr, nullptr);
+  if (h->world <= 1 || n == 0) {
+    if (local_status != AB_OK) {
+      return local_status;
+    }
+  } else {
     // assemble: every observation was written by exactly one rank, the others hold zero
     Scope sc(h);
     void *d = nullptr;
-    const int64_t cnt = 2 * n + 1;
+    const int64_t cnt = 2 * n + 3; // means, variances, score, #ranks not PD, #ranks failed otherwise
     AB_TRY(sc.alloc(static_cast<size_t>(cnt) * sizeof(double), &d));
     double *buf = static_cast<double *>(d);
     std::vector<double> host(static_cast<size_t>(cnt), 0.);
-    std::copy(mean, mean + n, host.begin());
-    if (what == AB_PREDICT_MARGINAL) {
-      std::copy(var, var + n, host.begin() + n);
+    if (local_status == AB_OK) {
+      std::copy(mean, mean + n, host.begin());
+      if (what == AB_PREDICT_MARGINAL) {
+        std::copy(var, var + n, host.begin() + n);
+      }
+      host[static_cast<size_t>(2 * n)] = local_score;
+    } else {
+      host[static_cast<size_t>(2 * n + (local_status == AB_ERR_NOT_PD ? 1 : 2))] = 1.;
     }
-    host[static_cast<size_t>(2 * n)] = local_score;
     AB_CUDA(cudaMemcpyAsync(buf, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice,
                             h->stream));
     AB_TRY(dist_allreduce_sum(h, buf, cnt));
     AB_TRY(download_bytes(h, buf, host.size() * sizeof(double), host.data()));
+    if (local_status != AB_OK) {
+      return local_status; // ab_last_error() already describes it
+    }
+    if (host[static_cast<size_t>(2 * n + 1)] > 0.) {
+      set_error("a held-out block of the inverse covariance is not positive definite on another rank");
+      return AB_ERR_NOT_PD;
+    }
+    if (host[static_cast<size_t>(2 * n + 2)] > 0.) {
+      set_error("ab_dist_gp_cv failed on another rank");
+      return AB_ERR_CUDA;
+    }
     std::copy(host.begin(), host.begin() + n, mean);
     if (what == AB_PREDICT_MARGINAL) {
       std::copy(host.begin() + n, host.begin() + 2 * n, var);

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -396,21 +397,55 @@ int ab_factor_inverse_blocks(ab_handle h, ab_factor f, const int64_t *indices,
   return AB_OK;
 }
 
-__global__ void export_packed_kernel(const double *L, int64_t ld, int64_t n, double *out) {
-  // out(i,j) = L(i,j) / L(j,j) for i > j ; out(j,j) = L(j,j)^2 ; out(i,j) = L-like mirror for i < j
+// Columns [c0, c0 + w) of a dense n x n host view of the factor, written to a packed n x w panel.
+//   mode 0  Eigen's packed LDLT (serializable_ldlt.hpp / cereal layout): strict lower = unit L, diagonal
+//           = D, strict upper = the transpose (Eigen's matrixLDLT is read through triangular views)
+//   mode 1  sqrt_transpose(): D^1/2 (P^T L)^T = L_chol^T, upper triangular, zeros below
+__global__ void export_panel_kernel(const double *L, int64_t ld, int64_t n, int64_t c0, int64_t w,
+                                    int mode, double *out) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t j = blockIdx.y;
-  if (i >= n) {
+  const int64_t jl = blockIdx.y;
+  const int64_t j = c0 + jl;
+  if (i >= n || jl >= w) {
     return;
   }
-  const double ljj = L[j + j * ld];
-  if (i > j) {
-    out[i + j * n] = L[i + j * ld] / ljj;
-  } else if (i == j) {
-    out[i + j * n] = ljj * ljj;
+  double v;
+  if (mode == 0) {
+    const double ljj = L[j + j * ld];
+    if (i > j) {
+      v = L[i + j * ld] / ljj;
+    } else if (i == j) {
+      v = ljj * ljj;
+    } else {
+      v = L[j + i * ld] / L[i + i * ld];
+    }
   } else {
-    out[i + j * n] = L[j + i * ld] / L[i + i * ld]; // symmetric fill, as Eigen's matrixLDLT is read via views
+    v = i <= j ? L[j + i * ld] : 0.;
   }
+  out[i + jl * n] = v;
+}
+
+// Streams the n x n host matrix in column panels through a bounded device buffer (no n^2 scratch: the
+// headline size n = 65 536 is 34 GB of factor already).
+static int export_dense(ab_handle h, ab_factor f, int mode, double *host) {
+  const int64_t n = f->n;
+  int64_t w = std::max<int64_t>(1, (int64_t(256) << 20) / (n * static_cast<int64_t>(sizeof(double))));
+  if (const char *e = std::getenv("AB_EXPORT_PANEL_COLS")) { // test hook: force several panels
+    w = std::max<int64_t>(1, std::atoll(e));
+  }
+  w = std::min<int64_t>(std::min<int64_t>(w, n), 65535);
+  Scope sc(h);
+  void *d = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(n) * w * sizeof(double), &d));
+  for (int64_t c0 = 0; c0 < n; c0 += w) {
+    const int64_t wc = std::min(w, n - c0);
+    const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(wc));
+    export_panel_kernel<<<grid, 256, 0, h->stream>>>(f->m->d, f->m->ld, n, c0, wc, mode,
+                                                     static_cast<double *>(d));
+    AB_LAUNCHED(h);
+    AB_TRY(download_bytes(h, d, static_cast<size_t>(n) * wc * sizeof(double), host + c0 * n));
+  }
+  return AB_OK;
 }
 
 int ab_factor_export_packed(ab_handle h, ab_factor f, double *LD, int64_t *transpositions) {
@@ -421,22 +456,87 @@ int ab_factor_export_packed(ab_handle h, ab_factor f, double *LD, int64_t *trans
   if (n == 0) {
     return AB_OK;
   }
-  Scope sc(h);
-  void *d = nullptr;
-  AB_TRY(sc.alloc(static_cast<size_t>(n) * n * sizeof(double), &d));
-  for (int64_t c0 = 0; c0 < n; c0 += 65535) {
-    const int64_t nc = std::min<int64_t>(65535, n - c0);
-    AB_REQUIRE(c0 == 0, "export_packed supports n <= 65535");
-    const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(nc));
-    export_packed_kernel<<<grid, 256, 0, h->stream>>>(f->m->d, f->m->ld, n,
-                                                      static_cast<double *>(d));
-    AB_LAUNCHED(h);
-  }
-  AB_TRY(download_bytes(h, d, static_cast<size_t>(n) * n * sizeof(double), LD));
+  AB_TRY(export_dense(h, f, 0, LD));
   if (transpositions != nullptr) {
     std::iota(transpositions, transpositions + n, int64_t(0));
   }
   return AB_OK;
+}
+
+int ab_factor_sqrt_transpose(ab_handle h, ab_factor f, double *out) {
+  AB_REQUIRE(h != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  return f->n == 0 ? AB_OK : export_dense(h, f, 1, out);
+}
+
+__global__ void diag_kernel(const double *L, int64_t ld, int64_t n, double *out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    out[i] = L[i + i * ld];
+  }
+}
+
+int ab_factor_diagonal_sqrt(ab_handle h, ab_factor f, double *out) {
+  AB_REQUIRE(h != nullptr && out != nullptr, "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  const int64_t n = f->n;
+  if (n == 0) {
+    return AB_OK;
+  }
+  Scope sc(h);
+  void *d = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(n) * sizeof(double), &d));
+  diag_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, h->stream>>>(
+      f->m->d, f->m->ld, n, static_cast<double *>(d));
+  AB_LAUNCHED(h);
+  return download_bytes(h, d, static_cast<size_t>(n) * sizeof(double), out);
+}
+
+int ab_factor_sqrt_product(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out) {
+  AB_REQUIRE(h != nullptr && (rhs != nullptr || nrhs == 0) && (out != nullptr || nrhs == 0) &&
+                 nrhs >= 0,
+             "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  if (nrhs == 0 || f->n == 0) {
+    return AB_OK;
+  }
+  Scope sc(h);
+  timings_reset(h);
+  ab_matrix_s *X = nullptr, *Y = nullptr;
+  AB_TRY(upload(h, rhs, f->n, nrhs, &X));
+  sc.own(X);
+  AB_TRY(matrix_new(h, f->n, nrhs, &Y));
+  sc.own(Y);
+  phase_begin(h, PH_SOLVE);
+  AB_TRY(trmm_left_lower(h, view(f->m), f->n, false, view(X), view(Y), nrhs));
+  phase_end(h, PH_SOLVE);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return download(h, Y, 0, 0, f->n, nrhs, out);
+}
+
+int ab_factor_sqrt_transpose_solve(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs,
+                                   double *out) {
+  AB_REQUIRE(h != nullptr && (rhs != nullptr || nrhs == 0) && (out != nullptr || nrhs == 0) &&
+                 nrhs >= 0,
+             "null");
+  Lock lock(h);
+  AB_TRY(require_usable(f));
+  if (nrhs == 0 || f->n == 0) {
+    return AB_OK;
+  }
+  Scope sc(h);
+  timings_reset(h);
+  ab_matrix_s *X = nullptr;
+  AB_TRY(upload(h, rhs, f->n, nrhs, &X));
+  sc.own(X);
+  phase_begin(h, PH_SOLVE);
+  AB_TRY(trsm_left_lower_T(h, view(f->m), f->dinv, f->n, view(X), nrhs));
+  phase_end(h, PH_SOLVE);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  return download(h, X, 0, 0, f->n, nrhs, out);
 }
 
 // ---- exact GP ---------------------------------------------------------------------------------
@@ -713,7 +813,20 @@ int gp_cv_impl(ab_handle_s *h, ab_factor_s *f, const double *y, const double *in
     maxg = std::max(maxg, offsets[g + 1] - offsets[g]);
   }
   const bool sharded = stride > 1;
-  const bool pure_loo = maxg == 1 && total == n && ngroups == n;
+  bool pure_loo = maxg == 1 && total == n && ngroups == n;
+  if (pure_loo) {
+    // the element-wise fast path indexes host vectors by group: the indices must be a permutation of
+    // 0..n-1 (anything else — out of range, duplicates — takes the general path, which range-checks)
+    std::vector<char> seen(static_cast<size_t>(n), 0);
+    for (int64_t g = 0; g < n && pure_loo; ++g) {
+      const int64_t idx = indices[offsets[g]];
+      if (idx < 0 || idx >= n || seen[static_cast<size_t>(idx)]) {
+        pure_loo = false;
+      } else {
+        seen[static_cast<size_t>(idx)] = 1;
+      }
+    }
+  }
   Scope sc(h);
   ab_matrix_s *W = nullptr;
   if (!sharded) {

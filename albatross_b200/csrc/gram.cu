@@ -29,25 +29,25 @@ static bool leaf_to_dev_raw(const ab_op &o, DevOp *d) {
   const double l = o.p0;
   switch (o.op) {
   case AB_OP_SQUARED_EXPONENTIAL:
-    d->kind = l > 0. ? DK_RADIAL : DK_ZERO;
+    d->kind = l <= 0. ? DK_ZERO : DK_RADIAL; // a NaN length scale propagates (radial.hpp:28-30)
     d->a2 = -1. / (l * l);
     d->amp = o.p1 * o.p1;
     return true;
   case AB_OP_EXPONENTIAL:
-    d->kind = l > 0. ? DK_RADIAL : DK_ZERO;
+    d->kind = l <= 0. ? DK_ZERO : DK_RADIAL; // a NaN length scale propagates (radial.hpp:28-30)
     d->flags = DF_USES_DIST;
     d->a1 = -1. / l;
     d->amp = o.p1 * o.p1;
     return true;
   case AB_OP_MATERN32:
-    d->kind = l > 0. ? DK_RADIAL : DK_ZERO;
+    d->kind = l <= 0. ? DK_ZERO : DK_RADIAL; // a NaN length scale propagates (radial.hpp:28-30)
     d->flags = DF_USES_DIST | DF_POLY_D1;
     d->a1 = -std::sqrt(3.) / l;
     d->b1 = std::sqrt(3.) / l;
     d->amp = o.p1 * o.p1;
     return true;
   case AB_OP_MATERN52:
-    d->kind = l > 0. ? DK_RADIAL : DK_ZERO;
+    d->kind = l <= 0. ? DK_ZERO : DK_RADIAL; // a NaN length scale propagates (radial.hpp:28-30)
     d->flags = DF_USES_DIST | DF_POLY_D1 | DF_POLY_D2;
     d->a1 = -std::sqrt(5.) / l;
     d->b1 = std::sqrt(5.) / l;

@@ -255,6 +255,58 @@ int trsm_left_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, 
   return trsm_left_lower_T(h, L, dinv, n1, X, p);
 }
 
+// Y[0:nb, c] = tril(L) X[0:nb, c] or tril(L)^T X[0:nb, c] for one LEAF-sized diagonal block; thread =
+// (row, column of a 4-column group).
+__global__ void __launch_bounds__(256)
+trmm_leaf_kernel(const double *L, int64_t ldl, int nb, int trans, const double *X, int64_t ldx,
+                 double *Y, int64_t ldy, int64_t p) {
+  __shared__ double s[LEAF * LS];
+  for (int idx = threadIdx.x; idx < LEAF * LEAF; idx += blockDim.x) {
+    const int r = idx % LEAF, c = idx / LEAF;
+    s[r * LS + c] = (r < nb && c <= r) ? L[r + c * ldl] : 0.;
+  }
+  __syncthreads();
+  const int r = threadIdx.x & (LEAF - 1);
+  const int64_t c = blockIdx.x * static_cast<int64_t>(4) + (threadIdx.x >> 6);
+  if (r >= nb || c >= p) {
+    return;
+  }
+  const double *x = X + c * ldx;
+  double acc = 0.;
+  if (!trans) {
+    for (int t = 0; t <= r; ++t) {
+      acc = fma(s[r * LS + t], x[t], acc);
+    }
+  } else {
+    for (int t = r; t < nb; ++t) {
+      acc = fma(s[t * LS + r], x[t], acc);
+    }
+  }
+  Y[r + c * ldy] = acc;
+}
+
+int trmm_left_lower(ab_handle_s *h, MatView L, int64_t n, bool trans, MatView X, MatView Y,
+                    int64_t p) {
+  if (n <= 0 || p <= 0) {
+    return AB_OK;
+  }
+  if (n <= LEAF) {
+    trmm_leaf_kernel<<<static_cast<unsigned>((p + 3) / 4), 256, 0, h->stream>>>(
+        L.p, L.ld, static_cast<int>(n), trans ? 1 : 0, X.p, X.ld, Y.p, Y.ld, p);
+    AB_LAUNCHED(h);
+    return AB_OK;
+  }
+  const int64_t n1 = split(n);
+  const int64_t n2 = n - n1;
+  AB_TRY(trmm_left_lower(h, L, n1, trans, X, Y, p));
+  AB_TRY(trmm_left_lower(h, L.sub(n1, n1), n2, trans, X.sub(n1, 0), Y.sub(n1, 0), p));
+  if (!trans) { // Y2 += L21 X1
+    return gemm(h, 0u, n2, p, n1, 1., L.sub(n1, 0), X, 1., Y.sub(n1, 0));
+  }
+  // Y1 += L21^T X2
+  return gemm(h, GEMM_TRANS_A, n1, p, n2, 1., L.sub(n1, 0), X.sub(n1, 0), 1., Y);
+}
+
 static int potrf_rec(ab_handle_s *h, MatView A, int64_t n, double *dinv, int64_t offset,
                      int *d_bad) {
   if (n <= LEAF) {

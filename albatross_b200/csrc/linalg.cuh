@@ -47,6 +47,10 @@ int trsm_left_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, 
 int trsm_right_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, MatView X,
                        int64_t m);
 
+// Y <- L X (trans == false) or Y <- L^T X (trans == true), n x p; only the lower triangle of L is read
+// (the strict upper triangle of an in-place factor holds stale data).  Y must not alias X.
+int trmm_left_lower(ab_handle_s *h, MatView L, int64_t n, bool trans, MatView X, MatView Y, int64_t p);
+
 // out[0] = sum_i 2 log(L_ii)
 int logdet_chol(ab_handle_s *h, MatView L, int64_t n, double *d_out);
 // out[0] = sum_i a_i * b_i

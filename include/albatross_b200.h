@@ -189,9 +189,21 @@ AB_API int ab_factor_inverse_blocks(ab_handle h, ab_factor f, const int64_t *ind
                              const int64_t *offsets, int64_t ngroups, double *out);
 /*
  * Materialises the factor in Eigen::SerializableLDLT's packed layout: strict lower = unit L,
- * diagonal = D, transpositions = identity (src/cereal/serializable_ldlt.hpp:18-32).
+ * diagonal = D, transpositions = identity (src/cereal/serializable_ldlt.hpp:18-32).  Streamed in column
+ * panels through a bounded device buffer: works at any n the host can hold (n = 65 536 is 32 GiB).
  */
 AB_API int ab_factor_export_packed(ab_handle h, ab_factor f, double *LD, int64_t *transpositions);
+
+/* out = P^T L D^1/2 rhs = L_chol rhs.  SerializableLDLT::sqrt_product, serializable_ldlt.hpp:91-94. */
+AB_API int ab_factor_sqrt_product(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out);
+/* out = P^T L^-T D^-1/2 rhs = L_chol^-T rhs.  sqrt_transpose_solve, serializable_ldlt.hpp:123-126. */
+AB_API int ab_factor_sqrt_transpose_solve(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs,
+                                   double *out);
+/* out (n x n, column-major) = D^1/2 (P^T L)^T = L_chol^T, upper triangular.  sqrt_transpose, :111-115. */
+AB_API int ab_factor_sqrt_transpose(ab_handle h, ab_factor f, double *out);
+/* out[n] = sqrt(D_ii) = diag(L_chol).  diagonal_sqrt :74-84 (and, inverted, diagonal_sqrt_inverse :58-69;
+ * a usable factor has every D_ii > 0, so the reference's clamping of non-positive pivots never fires). */
+AB_API int ab_factor_diagonal_sqrt(ab_handle h, ab_factor f, double *out);
 
 /* ---- exact GP (src/models/gp.hpp) ---------------------------------------------------------- */
 

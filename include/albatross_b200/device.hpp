@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <limits>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -41,6 +42,30 @@ inline void check_status(int status, const char *what) {
 }
 
 #define ALBATROSS_B200_CHECK(call) ::albatross_b200::check_status((call), #call)
+
+// Policy for matrices that are not positive definite: the reference's diagonally pivoted
+// LDLT never fails — on a semi-definite or indefinite K it returns zero / negative pivots, and everything
+// computed from them (log-determinant, solves) is NaN or +-inf, which GenericTuner maps to an infinite
+// objective (src/tune/tune.hpp:164-166, :204-206).  The device factorisation is unpivoted and reports
+// AB_ERR_NOT_PD instead; the trait layer turns that status into the same observable result — NaN outputs
+// and is_positive_definite() == false — rather than aborting, so a tuner step into a bad region continues.
+// true: the call failed with AB_ERR_NOT_PD (the caller fills its outputs with NaN); any other non-zero
+// status is fatal as before.
+inline bool is_not_positive_definite(int status, const char *what) {
+  if (status == AB_ERR_NOT_PD) {
+    return true;
+  }
+  check_status(status, what);
+  return false;
+}
+#define ALBATROSS_B200_NOT_PD(call) ::albatross_b200::is_not_positive_definite((call), #call)
+
+inline double quiet_nan() { return std::numeric_limits<double>::quiet_NaN(); }
+inline void fill_nan(double *p, std::size_t n) {
+  for (std::size_t i = 0; p != nullptr && i < n; ++i) {
+    p[i] = quiet_nan();
+  }
+}
 
 // One handle per (process, device).  Models are copied liberally by the reference (FitModel stores
 // the model by value, the tuner copies it per evaluation: src/core/fit_model.hpp:112,
@@ -234,6 +259,9 @@ public:
 
   // serializable_ldlt.hpp:36 (isPositive()): every pivot was > 0.
   bool is_positive_definite() const {
+    if (get() == nullptr) {
+      return false;
+    }
     int64_t bad = -1;
     ALBATROSS_B200_CHECK(ab_factor_info(get(), &bad));
     return bad < 0;
@@ -255,6 +283,43 @@ public:
   MatrixXd sqrt_solve(const MatrixXd &rhs) const {
     MatrixXd out(rhs.rows(), rhs.cols());
     ALBATROSS_B200_CHECK(ab_factor_sqrt_solve(h(), get(), rhs.data(), rhs.cols(), out.data()));
+    return out;
+  }
+
+  // serializable_ldlt.hpp:91-94: P^T L D^1/2 rhs.
+  MatrixXd sqrt_product(const MatrixXd &rhs) const {
+    MatrixXd out(rhs.rows(), rhs.cols());
+    ALBATROSS_B200_CHECK(ab_factor_sqrt_product(h(), get(), rhs.data(), rhs.cols(), out.data()));
+    return out;
+  }
+
+  // serializable_ldlt.hpp:123-126: P^T L^-T D^-1/2 rhs.
+  MatrixXd sqrt_transpose_solve(const MatrixXd &rhs) const {
+    MatrixXd out(rhs.rows(), rhs.cols());
+    ALBATROSS_B200_CHECK(ab_factor_sqrt_transpose_solve(h(), get(), rhs.data(), rhs.cols(), out.data()));
+    return out;
+  }
+
+  // serializable_ldlt.hpp:111-115: D^1/2 (P^T L)^T as a dense upper-triangular matrix.
+  MatrixXd sqrt_transpose() const {
+    const Index n = rows();
+    MatrixXd out(n, n);
+    ALBATROSS_B200_CHECK(ab_factor_sqrt_transpose(h(), get(), out.data()));
+    return out;
+  }
+
+  // serializable_ldlt.hpp:74-84 / :58-69, returned as the diagonal's vector (the reference returns an
+  // Eigen::DiagonalMatrix; non-positive pivots, which it clamps to 0, cannot occur in a usable factor).
+  VectorXd diagonal_sqrt() const {
+    VectorXd out(rows());
+    ALBATROSS_B200_CHECK(ab_factor_diagonal_sqrt(h(), get(), out.data()));
+    return out;
+  }
+  VectorXd diagonal_sqrt_inverse() const {
+    VectorXd out = diagonal_sqrt();
+    for (Index i = 0; i < out.size(); ++i) {
+      out[i] = out[i] > 0. ? 1. / out[i] : 0.;
+    }
     return out;
   }
 

@@ -381,8 +381,12 @@ public:
     const std::shared_ptr<Device> dev = device();
     ab_factor factor = nullptr;
     const double *yvar = targets.has_covariance() ? targets.covariance.diagonal().data() : nullptr;
-    ALBATROSS_B200_CHECK(ab_gp_fit(dev->get(), prog.data(), static_cast<int>(prog.size()), f.data.data(),
-                                   f.n, f.dim, y.data(), yvar, &factor, information.data()));
+    // not positive definite: the (unusable) factor is still owned by the fit, so nothing leaks and
+    // is_positive_definite() reports it; information is NaN as the reference's would be
+    if (ALBATROSS_B200_NOT_PD(ab_gp_fit(dev->get(), prog.data(), static_cast<int>(prog.size()), f.data.data(),
+                                        f.n, f.dim, y.data(), yvar, &factor, information.data()))) {
+      fill_nan(information.data(), static_cast<std::size_t>(information.size()));
+    }
     return DeviceGPFit<FeatureType>(features, DeviceLDLT(dev, factor), std::move(information));
   }
 
@@ -440,8 +444,10 @@ public:
     VectorXd y(dataset.targets.mean);
     remove_mean(mean_function_, dataset.features, &y);
     double nll = 0.;
-    ALBATROSS_B200_CHECK(ab_gp_nll(device()->get(), prog.data(), static_cast<int>(prog.size()),
-                                   f.data.data(), f.n, f.dim, y.data(), &nll));
+    if (ALBATROSS_B200_NOT_PD(ab_gp_nll(device()->get(), prog.data(), static_cast<int>(prog.size()),
+                                        f.data.data(), f.n, f.dim, y.data(), &nll))) {
+      return quiet_nan(); // the tuner maps NaN to an infinite objective (tune.hpp:164-166)
+    }
     return -nll + this->prior_log_likelihood();
   }
 
@@ -527,12 +533,17 @@ protected:
     }
     // Note (gp.hpp:472-476): the held-out algebra works on the raw targets; the information vector
     // already accounts for the mean function.
-    ALBATROSS_B200_CHECK(ab_gp_cv_scores(
-        device()->get(), gp_fit.train_covariance.get(), dataset.targets.mean.data(),
-        gp_fit.information.data(), csr.indices.data(), csr.offsets.data(), csr.ngroups(), what,
-        raw.mean.data(), what == AB_PREDICT_MARGINAL ? raw.var.data() : nullptr,
-        what == AB_PREDICT_JOINT ? raw.joint.data() : nullptr, nullptr,
-        want_scores ? raw.scores.data() : nullptr));
+    if (ALBATROSS_B200_NOT_PD(ab_gp_cv_scores(
+            device()->get(), gp_fit.train_covariance.get(), dataset.targets.mean.data(),
+            gp_fit.information.data(), csr.indices.data(), csr.offsets.data(), csr.ngroups(), what,
+            raw.mean.data(), what == AB_PREDICT_MARGINAL ? raw.var.data() : nullptr,
+            what == AB_PREDICT_JOINT ? raw.joint.data() : nullptr, nullptr,
+            want_scores ? raw.scores.data() : nullptr))) {
+      fill_nan(raw.mean.data(), static_cast<std::size_t>(raw.mean.size()));
+      fill_nan(raw.var.data(), static_cast<std::size_t>(raw.var.size()));
+      fill_nan(raw.scores.data(), static_cast<std::size_t>(raw.scores.size()));
+      fill_nan(raw.joint.data(), raw.joint.size());
+    }
     return raw;
   }
 
@@ -555,16 +566,19 @@ protected:
     const PackedFeatures train = pack_features(gp_fit.train_features);
     const PackedFeatures test = pack_features(features);
     const ab_handle h = device()->get();
-    if (same) {
-      ALBATROSS_B200_CHECK(ab_gp_predict(h, gp_fit.train_covariance.get(), cross.data(),
-                                         static_cast<int>(cross.size()), train.data.data(), train.n, train.dim,
-                                         gp_fit.information.data(), test.data.data(), test.n, what, mean, var, cov));
-      return;
+    const int status =
+        same ? ab_gp_predict(h, gp_fit.train_covariance.get(), cross.data(), static_cast<int>(cross.size()),
+                             train.data.data(), train.n, train.dim, gp_fit.information.data(), test.data.data(),
+                             test.n, what, mean, var, cov)
+             : ab_gp_predict2(h, gp_fit.train_covariance.get(), cross.data(), static_cast<int>(cross.size()),
+                              prior.data(), static_cast<int>(prior.size()), train.data.data(), train.n, train.dim,
+                              gp_fit.information.data(), test.data.data(), test.n, what, mean, var, cov);
+    if (is_not_positive_definite(status, "ab_gp_predict")) { // a fit of a matrix that was not PD
+      const std::size_t p = static_cast<std::size_t>(test.n);
+      fill_nan(mean, p);
+      fill_nan(var, p);
+      fill_nan(cov, p * p);
     }
-    ALBATROSS_B200_CHECK(ab_gp_predict2(h, gp_fit.train_covariance.get(), cross.data(),
-                                        static_cast<int>(cross.size()), prior.data(),
-                                        static_cast<int>(prior.size()), train.data.data(), train.n, train.dim,
-                                        gp_fit.information.data(), test.data.data(), test.n, what, mean, var, cov));
   }
 
   static std::string default_name() { return "gaussian_process_regression"; }

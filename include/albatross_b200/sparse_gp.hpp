@@ -187,18 +187,23 @@ private:
     // :667-668), so y is not de-meaned; reproduced by not touching y here.
     const double *yvar = targets.has_covariance() ? targets.covariance.diagonal().data() : nullptr;
     const ab_handle h = this->device()->get();
+    bool not_pd = false;
     if (fit_out != nullptr) {
-      ALBATROSS_B200_CHECK(ab_sparse_fit2(
+      not_pd = ALBATROSS_B200_NOT_PD(ab_sparse_fit2(
           h, p_ff.data(), static_cast<int>(p_ff.size()), p_fu.data(), static_cast<int>(p_fu.size()), p_uu.data(),
           static_cast<int>(p_uu.size()), f.data.data(), f.n, f.dim, y.data(), yvar, fu.data.data(), fu.n,
           csr.indices.data(), csr.offsets.data(), csr.ngroups(), measurement_nugget_.value,
           inducing_nugget_.value, fit_out, information, log_likelihood));
     } else {
-      ALBATROSS_B200_CHECK(ab_sparse_log_likelihood2(
+      not_pd = ALBATROSS_B200_NOT_PD(ab_sparse_log_likelihood2(
           h, p_ff.data(), static_cast<int>(p_ff.size()), p_fu.data(), static_cast<int>(p_fu.size()), p_uu.data(),
           static_cast<int>(p_uu.size()), f.data.data(), f.n, f.dim, y.data(), yvar, fu.data.data(), fu.n,
           csr.indices.data(), csr.offsets.data(), csr.ngroups(), measurement_nugget_.value,
           inducing_nugget_.value, log_likelihood));
+    }
+    if (not_pd) { // K_uu or a block of A was not positive definite: NaN, as the reference's LDLT would yield
+      fill_nan(information, static_cast<std::size_t>(fu.n));
+      fill_nan(log_likelihood, 1);
     }
   }
 
@@ -208,6 +213,13 @@ private:
     const Program cross = this->covariance_function_.template program<U, FeatureType>();
     const Program prior = this->covariance_function_.template program<FeatureType, FeatureType>();
     const PackedFeatures test = pack_features(features);
+    if (fit.device_fit->f == nullptr) { // the fit met a matrix that was not positive definite
+      const std::size_t p = static_cast<std::size_t>(test.n);
+      fill_nan(mean, p);
+      fill_nan(var, p);
+      fill_nan(cov, p * p);
+      return;
+    }
     ALBATROSS_B200_CHECK(ab_sparse_predict2(fit.device_fit->dev->get(), fit.device_fit->f, cross.data(),
                                             static_cast<int>(cross.size()), prior.data(),
                                             static_cast<int>(prior.size()), test.data.data(), test.n, what, mean,

@@ -403,6 +403,54 @@ static void scenario_sparse() {
   EXPECT(R.rows() == 48 && R(5, 2) == 0.); // upper triangular
 }
 
+static void scenario_sparse_measurement_only() {
+  // the reference's standard sparse configuration (tests/lib/albatross/test/test_models.h:26-30,44-57):
+  // the noise sits behind measurement_only, so K_ff, K_fu and K_uu are three different programs
+  auto data = make_1d(2000, 9, 0., 10.);
+  dump("spmo.x", data.features);
+  dump("spmo.y", data.targets.mean);
+  auto cov = SE(1., 1.) + ab::measurement_only(ab::IndependentNoise<double>(0.1));
+  std::vector<double> test = ab::linspace(0.25, 9.75, 17);
+  dump("spmo.test", test);
+  auto fitc = ab::sparse_gp_from_covariance(cov, ab::LeaveOneOutGrouper(), ab::UniformlySpacedInducingPoints(40), "fitc");
+  const auto fitc_fit = fitc.fit(data);
+  dump("spmo.inducing", fitc_fit.get_fit().train_features);
+  dump("spmo.fitc.marginal", fitc_fit.predict(test).marginal());
+  dump("spmo.fitc.joint", fitc_fit.predict(test).joint());
+  dump("spmo.fitc.ll", fitc.log_likelihood(data) - fitc.prior_log_likelihood());
+  auto grouper = [](const double &x) { return static_cast<long>(std::floor(x * 2.)); };
+  auto pitc = ab::sparse_gp_from_covariance(cov, grouper, ab::UniformlySpacedInducingPoints(40), "pitc");
+  dump("spmo.pitc.marginal", pitc.fit(data).predict(test).marginal());
+  dump("spmo.pitc.ll", pitc.log_likelihood(data) - pitc.prior_log_likelihood());
+}
+
+static void scenario_not_positive_definite() {
+  // Duplicate points without a noise term: K is singular.  The reference's pivoted LDLT proceeds and its
+  // outputs are NaN / inf (GenericTuner maps a NaN objective to +inf, tune.hpp:164-166); the device reports
+  // AB_ERR_NOT_PD and the layer turns it into the same observable result instead of aborting.
+  std::vector<double> xs = {0., 1., 2., 2., 3., 1.};
+  VectorXd y(6);
+  for (Index i = 0; i < 6; ++i) {
+    y[i] = std::sin(xs[static_cast<std::size_t>(i)]);
+  }
+  ab::RegressionDataset<double> data(xs, y);
+  auto model = ab::gp_from_covariance(SE(1., 1.));
+  const auto fit_model = model.fit(data); // must not abort, must not leak the factor
+  EXPECT(!fit_model.get_fit().train_covariance.is_positive_definite());
+  EXPECT(std::isnan(fit_model.get_fit().information[0]));
+  const double ll = model.log_likelihood(data);
+  EXPECT(std::isnan(ll));
+  const auto pred = fit_model.predict(std::vector<double>{0.5, 1.5}).marginal();
+  EXPECT(std::isnan(pred.mean[0]) && std::isnan(pred.covariance.diagonal()[1]));
+  ab::LeaveOneOutLikelihood<> loo;
+  EXPECT(std::isnan(loo(data, model)));
+  dump("notpd.ll_is_nan", std::isnan(ll) ? 1. : 0.);
+  // many failed objective evaluations in a row (a tuner wandering in a bad region) recycle the matrix
+  for (int rep = 0; rep < 50; ++rep) {
+    EXPECT(std::isnan(model.log_likelihood(data)));
+  }
+}
+
 int main(int argc, char **argv) {
   if (argc >= 2 && std::strcmp(argv[1], "host") == 0) {
     host_checks();
@@ -421,6 +469,8 @@ int main(int argc, char **argv) {
       scenario_measurement_only();
       scenario_3d();
       scenario_sparse();
+      scenario_sparse_measurement_only();
+      scenario_not_positive_definite();
       const ab_phase_times t = ab::Device::default_device()->timings();
       dump("kernel_launches", static_cast<double>(t.kernel_launches));
     } catch (const ab::device_error &e) {

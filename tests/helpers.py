@@ -1,4 +1,6 @@
 """Shared test data: the reference's covariance menu (oracle/ref_shim/ref_common.h) and generators."""
+import os
+
 import numpy as np
 
 from oracle.oracle import menu_program
@@ -34,4 +36,8 @@ def assert_close(a, b, rtol, what=""):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, (what, a.shape, b.shape)
     err = rel_err(a, b)
+    log = os.environ.get("AB_ERR_LOG")  # achieved errors, recorded for profiles/ (one line per check)
+    if log:
+        with open(log, "a") as fh:
+            fh.write(f"{os.environ.get('PYTEST_CURRENT_TEST', '?').split(' ')[0]}\t{what}\t{err:.3e}\t{rtol:.1e}\n")
     assert err <= rtol, f"{what}: relative error {err:.3e} > {rtol:.1e}"

@@ -2,7 +2,7 @@
 reference user writes code (gp_from_covariance, fit, predict().marginal(), log_likelihood,
 cross_validate(), sparse_gp_from_covariance, DeviceLDLT) and dumps inputs + results; here they are
 compared with the compiled reference (oracle/_ref) run on the very same inputs.
-Tolerances: 1e-9 relative for means / information / likelihoods (north_star), 1e-8 relative to the
+Tolerances: 1e-9 relative for means / information / likelihoods (north_star), 1e-9 relative to the
 prior scale for variances (formed by cancellation in the reference as well), 4e-15 for Gram entries."""
 import os
 import subprocess
@@ -54,10 +54,10 @@ def test_sinc_fit_predict_nll(dumped):
     mean, var, _ = Ref.gp_predict(cid, p, x, y, d["sinc.grid"], 1)
     assert_close(d["sinc.predict.mean"], mean, RTOL, "mean()")
     assert_close(d["sinc.predict.marginal.mean"], mean, RTOL, "marginal().mean")
-    assert np.max(np.abs(d["sinc.predict.marginal.var"] - var)) <= 1e-8 * (5.7 ** 2 + 1.0)
+    assert np.max(np.abs(d["sinc.predict.marginal.var"] - var)) <= 1e-9 * (5.7 ** 2 + 1.0)
     mean, _, cov = Ref.gp_predict(cid, p, x, y, d["sinc.few"], 2)
     assert_close(d["sinc.predict.joint.mean"], mean, RTOL, "joint().mean")
-    assert np.max(np.abs(d["sinc.predict.joint.cov"].reshape(5, 5).T - cov)) <= 1e-8 * (5.7 ** 2 + 1.0)
+    assert np.max(np.abs(d["sinc.predict.joint.cov"].reshape(5, 5).T - cov)) <= 1e-9 * (5.7 ** 2 + 1.0)
     nll, _ = Ref.gp_nll(cid, p, x, y)
     assert abs(d["sinc.nll"][0] - nll) <= RTOL * abs(nll)
     nll, _ = Ref.gp_nll(cid, [2.0, 5.7, 0.5], x, y)
@@ -71,7 +71,7 @@ def test_sinc_leave_one_out(dumped):
     mean, var, _, score = Ref.gp_cv(cid, p, x, y, 0, what=1, want_score=True)
     assert_close(d["sinc.loo.marginal.mean"], mean, RTOL, "LOO mean")
     assert_close(d["sinc.loo.mean"], mean, RTOL, "LOO mean()")
-    assert_close(d["sinc.loo.marginal.var"], var, 1e-8, "LOO variance")
+    assert_close(d["sinc.loo.marginal.var"], var, 1e-9, "LOO variance")
     # LeaveOneOutLikelihood<> = sum of per-point joint NLLs - prior ll (prior ll = 0 for these priors)
     assert abs(d["sinc.loo.likelihood"][0] - score) <= RTOL * abs(score)
     assert abs(d["sinc.loo.likelihood_marginal"][0] - score) <= RTOL * abs(score)
@@ -91,9 +91,9 @@ def test_sinc_grouped_cross_validation(dumped):
     assert np.array_equal(sizes, np.diff(offsets))
     mean, var, _, _ = Ref.gp_cv(cid, p, x, y, 1, 8.0, what=1)
     assert_close(d["sinc.cv.marginal.mean"], mean, RTOL, "grouped mean")
-    assert_close(d["sinc.cv.marginal.var"], var, 1e-8, "grouped variance")
+    assert_close(d["sinc.cv.marginal.var"], var, 1e-9, "grouped variance")
     mean2, _, joint, score = Ref.gp_cv(cid, p, x, y, 1, 8.0, what=2, group_sizes=sizes, want_score=True)
-    assert_close(d["sinc.cv.joint_blocks"], joint, 1e-8, "joint blocks")
+    assert_close(d["sinc.cv.joint_blocks"], joint, 1e-9, "joint blocks")
     assert_close(d["sinc.cv.group_means"], mean2[indices], RTOL, "group means")
     # per-group scores = the reference's negative_log_likelihood(joint_g - truth_g)
     at, want = 0, []
@@ -102,9 +102,9 @@ def test_sinc_grouped_cross_validation(dumped):
         cov = joint[at:at + k * k].reshape(k, k).T
         at += k * k
         want.append(Ref.nll_dense(mean2[idx] - y[idx], cov))
-    assert_close(d["sinc.cv.scores"], np.array(want), 1e-8, "scores()")
-    assert abs(d["sinc.cv.scores"].sum() - score) <= 1e-8 * abs(score)
-    assert abs(d["sinc.cv.logo_likelihood"][0] - score) <= 1e-8 * abs(score)
+    assert_close(d["sinc.cv.scores"], np.array(want), 1e-9, "scores()")
+    assert abs(d["sinc.cv.scores"].sum() - score) <= 1e-9 * abs(score)
+    assert abs(d["sinc.cv.logo_likelihood"][0] - score) <= 1e-9 * abs(score)
 
 
 def test_sinc_targets_with_measurement_variance(dumped):
@@ -122,7 +122,7 @@ def test_sinc_targets_with_measurement_variance(dumped):
         # points' own measurement variance (they were inside K + diag(yvar) at the fit), and the
         # reference's metric then adds truth.covariance once more (prediction_metrics.hpp:112-118)
         want = Ref.nll_dense(mean - y[held], cov + 2.0 * np.diag(yvar[held]))
-        assert abs(d["sinc.noisy.scores"][g] - want) <= 1e-7 * abs(want), (g, d["sinc.noisy.scores"][g], want)
+        assert abs(d["sinc.noisy.scores"][g] - want) <= 1e-9 * abs(want), (g, d["sinc.noisy.scores"][g], want)
 
 
 def test_measurement_only(dumped):
@@ -132,12 +132,12 @@ def test_measurement_only(dumped):
     assert_close(d["meas.information"], Ref.gp_fit(10, p, x, y)["information"], RTOL, "information")
     mean, var, _ = Ref.gp_predict(10, p, x, y, t, 1)
     assert_close(d["meas.predict.marginal.mean"], mean, RTOL)
-    assert np.max(np.abs(d["meas.predict.marginal.var"] - var)) <= 1e-8 * 4.0
+    assert np.max(np.abs(d["meas.predict.marginal.var"] - var)) <= 1e-9 * 4.0
     mean, _, cov = Ref.gp_predict(10, p, x, y, t, 2)
-    assert np.max(np.abs(d["meas.predict.joint.cov"].reshape(5, 5).T - cov)) <= 1e-8 * 4.0
+    assert np.max(np.abs(d["meas.predict.joint.cov"].reshape(5, 5).T - cov)) <= 1e-9 * 4.0
     mean, var, _ = Ref.gp_predict(10, p, x, y, t, 5)  # predict_with_measurement_noise
     assert_close(d["meas.predict_with_noise.marginal.mean"], mean, RTOL)
-    assert np.max(np.abs(d["meas.predict_with_noise.marginal.var"] - var)) <= 1e-8 * 4.0
+    assert np.max(np.abs(d["meas.predict_with_noise.marginal.var"] - var)) <= 1e-9 * 4.0
     # the noise term is present only between measurements
     assert np.all(d["meas.predict_with_noise.marginal.var"] - d["meas.predict.marginal.var"] > 0.08)
     nll, _ = Ref.gp_nll(10, p, x, y)
@@ -161,7 +161,7 @@ def test_3d_gram_and_gp(dumped):
     t = d["v3.test"].reshape(-1, 3)
     mean, _, cov = Ref.gp_predict(8, p8, x, y, t, 2)
     assert_close(d["v3.predict.joint.mean"], mean, RTOL)
-    assert np.max(np.abs(d["v3.predict.joint.cov"].reshape(10, 10).T - cov)) <= 1e-8 * 2.75
+    assert np.max(np.abs(d["v3.predict.joint.cov"].reshape(10, 10).T - cov)) <= 1e-9 * 2.75
     nll, _ = Ref.gp_nll(8, p8, x, y)
     assert abs(d["v3.nll"][0] - nll) <= RTOL * abs(nll)
     p9 = [2.0, 1.5, 3.0, 0.7, 1.5, 0.9, 1.1, 0.2]
@@ -196,11 +196,56 @@ def test_sparse_gp(dumped):
     assert np.array_equal(d["sparse.inducing"], u)  # bit-exact: same accumulation as linspace
     want = Ref.sparse_gp(6, p, x, y, u, 0, test=t, what=1, want_ll=True)
     assert_close(d["sparse.fitc.marginal.mean"], want["mean"], RTOL, "FITC mean")
-    assert np.max(np.abs(d["sparse.fitc.marginal.var"] - want["var"])) <= 1e-8
+    assert np.max(np.abs(d["sparse.fitc.marginal.var"] - want["var"])) <= 1e-9
     assert abs(d["sparse.fitc.ll"][0] - want["ll"]) <= RTOL * abs(want["ll"])
     wj = Ref.sparse_gp(6, p, x, y, u, 0, test=t, what=2)
-    assert np.max(np.abs(d["sparse.fitc.joint.cov"].reshape(19, 19).T - wj["cov"])) <= 1e-8
+    assert np.max(np.abs(d["sparse.fitc.joint.cov"].reshape(19, 19).T - wj["cov"])) <= 1e-9
     want = Ref.sparse_gp(6, p, x, y, u, 2, 2.0, test=t, what=1, want_ll=True)
     assert_close(d["sparse.pitc.marginal.mean"], want["mean"], RTOL, "PITC mean")
-    assert np.max(np.abs(d["sparse.pitc.marginal.var"] - want["var"])) <= 1e-8
+    assert np.max(np.abs(d["sparse.pitc.marginal.var"] - want["var"])) <= 1e-9
     assert abs(d["sparse.pitc.ll"][0] - want["ll"]) <= RTOL * abs(want["ll"])
+
+
+def test_sparse_gp_measurement_only(dumped):
+    """SE + measurement_only(noise): the reference's standard sparse configuration
+    (tests/lib/albatross/test/test_models.h:26-30), three covariance programs on the device."""
+    d = dumped
+    x, y, t = d["spmo.x"], d["spmo.y"], d["spmo.test"]
+    p = [1.0, 1.0, 0.1]
+    u = Ref.uniform_inducing_points(x, 40)
+    assert np.array_equal(d["spmo.inducing"], u)
+    want = Ref.sparse_gp(10, p, x, y, u, 0, test=t, what=1, want_ll=True)
+    assert_close(d["spmo.fitc.marginal.mean"], want["mean"], RTOL, "FITC mean")
+    assert np.max(np.abs(d["spmo.fitc.marginal.var"] - want["var"])) <= RTOL
+    assert abs(d["spmo.fitc.ll"][0] - want["ll"]) <= RTOL * abs(want["ll"])
+    wj = Ref.sparse_gp(10, p, x, y, u, 0, test=t, what=2)
+    assert np.max(np.abs(d["spmo.fitc.joint.cov"].reshape(17, 17).T - wj["cov"])) <= RTOL
+    want = Ref.sparse_gp(10, p, x, y, u, 2, 2.0, test=t, what=1, want_ll=True)
+    assert_close(d["spmo.pitc.marginal.mean"], want["mean"], RTOL, "PITC mean")
+    assert np.max(np.abs(d["spmo.pitc.marginal.var"] - want["var"])) <= RTOL
+    assert abs(d["spmo.pitc.ll"][0] - want["ll"]) <= RTOL * abs(want["ll"])
+
+
+def test_not_positive_definite_policy(dumped):
+    """A singular K (duplicate points, no noise) yields NaN outputs, not an abort."""
+    assert dumped["notpd.ll_is_nan"][0] == 1.0
+
+
+def test_eigen_typed_build_matches_stand_in_types(dumped, tmp_path):
+    """The same source compiled against the reference's vendored Eigen (Eigen::MatrixXd / VectorXd and
+    Eigen-vector features instead of the stand-in types; tests/cpp/Makefile builds it where /root/reference
+    exists and the binary travels to the GPU box) must produce the same numbers on the B200, bit for bit:
+    the layer only moves column-major doubles through the C ABI."""
+    exe = EXE + "_eigen"
+    if not os.path.exists(exe):
+        pytest.fail("tests/cpp/trait_layer_check_eigen missing: run __graft_entry__.build() where "
+                    "/root/reference exists")
+    path = str(tmp_path / "eigen.txt")
+    res = subprocess.run([exe, "gpu", path], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout + res.stderr
+    e = _parse(path)
+    assert set(e) == set(dumped)
+    for key, val in dumped.items():
+        if key == "kernel_launches":
+            continue
+        assert np.array_equal(val, e[key], equal_nan=True), key

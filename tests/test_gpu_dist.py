@@ -93,8 +93,8 @@ def test_cv_shards_sum_to_full(handle, grouper):
             vs += v_
             ss += s_
         assert_close(ms, want_mean, RTOL, "sharded means")
-        assert_close(vs, want_var, 1e-8, "sharded variances")
-        assert abs(ss - want_score) <= 1e-8 * abs(want_score)
+        assert_close(vs, want_var, 1e-9, "sharded variances")
+        assert abs(ss - want_score) <= 1e-9 * abs(want_score)
     f.free()
 
 

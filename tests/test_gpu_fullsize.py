@@ -102,8 +102,8 @@ def test_loo_cv_config4_full_size(handle):
     E[sample, np.arange(len(sample))] = 1.0
     Kinv_cols = f.solve(E)
     d = Kinv_cols[sample, np.arange(len(sample))]
-    assert_close(var[sample], 1.0 / d, 1e-8, "LOO variance")
-    assert_close(mean[sample], y[sample] - info[sample] / d, 1e-8, "LOO mean")
+    assert_close(var[sample], 1.0 / d, 1e-9, "LOO variance")
+    assert_close(mean[sample], y[sample] - info[sample] / d, 1e-9, "LOO mean")
     # leave-one-group-out, grouper int(x) % 8 (bench_loo_cv.cc:95-105): for each group g
     #   (K^-1)_gg (y_g - mean_g) = alpha_g, checked with one solve per group
     keys = x.astype(np.int64) % 8
@@ -120,5 +120,5 @@ def test_loo_cv_config4_full_size(handle):
         r = np.zeros(n)
         r[members] = y[members] - gmean[members]
         z = f.solve(r.reshape(-1, 1)).ravel()
-        assert_close(z[members], info[members], 1e-7, f"group {g} conditional mean")
+        assert_close(z[members], info[members], 1e-9, f"group {g} conditional mean")
     f.free()

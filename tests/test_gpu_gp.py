@@ -40,6 +40,48 @@ def test_factor_solve_logdet(handle, n):
     assert_close((L * np.diag(LD)) @ L.T, A, 1e-12, "L D L^T")
 
 
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 333, 1000])
+def test_sqrt_surface_identities(handle, n):
+    """sqrt_product / sqrt_transpose / sqrt_transpose_solve / diagonal_sqrt
+    (src/eigen/serializable_ldlt.hpp:58-126).  The square root is representation dependent (the reference's
+    is P^T L D^1/2 with its pivot order), so parity is what the reference's own test checks
+    (tests/test_serializable_ldlt.cc:58-85): S S^T = A, sqrt_solve(S) = I, sqrt_transpose_solve(S^T) = I."""
+    A = spd(n, seed=7 * n + 1)
+    f = handle.potrf(handle.upload(A))
+    eye = np.eye(n)
+    S = f.sqrt_product(eye)
+    assert np.array_equal(S, np.tril(S))                      # unpivoted: the square root is lower triangular
+    assert_close(S @ S.T, A, 1e-12, "S S^T = A")
+    ST = f.sqrt_transpose()
+    assert np.array_equal(ST, S.T)                            # the same numbers, transposed
+    assert np.linalg.norm(eye - f.sqrt_solve(S)) <= 1e-12 * n
+    assert np.linalg.norm(eye - f.sqrt_transpose_solve(np.ascontiguousarray(ST))) <= 1e-12 * n
+    d = f.diagonal_sqrt()
+    assert np.array_equal(d, np.diag(S)) and np.all(d > 0.0)
+    rhs = np.random.default_rng(n).standard_normal((n, 4))
+    assert_close(f.sqrt_product(rhs), S @ rhs, 1e-13, "sqrt_product rhs")
+    assert_close(f.sqrt_product(rhs[:, 0]), S @ rhs[:, 0], 1e-13, "sqrt_product vector")
+    # K^-1 = S^-T S^-1: the two half solves compose to the full one
+    assert_close(f.sqrt_transpose_solve(f.sqrt_solve(rhs)), f.solve(rhs), 1e-12, "two half solves")
+
+
+def test_export_packed_streams_in_panels(handle, monkeypatch):
+    """ab_factor_export_packed goes through a bounded device buffer (no n^2 scratch); forced to 37-column
+    panels here, the result is the single-panel one bit for bit."""
+    n = 500
+    A = spd(n, seed=99)
+    f = handle.potrf(handle.upload(A))
+    LD1, _ = f.export_packed()
+    monkeypatch.setenv("AB_EXPORT_PANEL_COLS", "37")
+    LD2, tr = f.export_packed()
+    ST = f.sqrt_transpose()
+    monkeypatch.delenv("AB_EXPORT_PANEL_COLS")
+    assert np.array_equal(LD1, LD2) and np.array_equal(tr, np.arange(n))
+    assert np.array_equal(ST, f.sqrt_transpose())
+    L = np.tril(LD2, -1) + np.eye(n)
+    assert_close((L * np.diag(LD2)) @ L.T, A, 1e-12, "L D L^T")
+
+
 def test_ldlt_wrapper_fixture(handle, golden):
     _, ref = golden
     A, rhs = ref["ldlt_A"], ref["ldlt_rhs"]
@@ -57,7 +99,8 @@ def test_inverse_diagonal_and_blocks(handle, n):
     A = spd(n, seed=3 * n)
     f = handle.potrf(handle.upload(A))
     inv = np.linalg.inv(A)
-    assert_close(f.inverse_diagonal(), np.diag(inv), 1e-8)
+    # against numpy's explicit inverse: the reference's own tolerance (tests/test_serializable_ldlt.cc:41-46)
+    assert_close(f.inverse_diagonal(), np.diag(inv), 1e-8, "inverse diagonal vs numpy inv")
     rng = np.random.default_rng(n)
     perm = rng.permutation(n)
     groups = [perm[: n // 3], perm[n // 3: n // 3 + 1], perm[n // 3 + 1:]]
@@ -91,6 +134,30 @@ def test_not_positive_definite_is_reported(handle):
     B[150, 20] = np.nan
     f = handle.potrf(handle.upload(B), allow_not_pd=True)
     assert not f.is_positive_definite()
+
+
+def test_loo_fast_path_validates_indices(handle):
+    """n singleton groups take an element-wise fast path only when their indices are a permutation of
+    0..n-1; out-of-range indices are rejected, duplicates go through the general (range-checked) path."""
+    ops, pp = prog(6)
+    n = 90
+    x = features(n, 1, 5).ravel()
+    y = targets(x)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    offsets = np.arange(n + 1, dtype=np.int64)
+    good = np.arange(n, dtype=np.int64)
+    m0, v0, _, _ = handle.gp_cv(f, y, info, offsets, good, MARGINAL)
+    bad = good.copy()
+    bad[5] = n + 3
+    with pytest.raises(capi.AbError) as err:
+        handle.gp_cv(f, y, info, offsets, bad, MARGINAL)
+    assert err.value.status == 1  # AB_ERR_INVALID
+    dup = good.copy()
+    dup[7] = 6                    # observation 6 held out twice, observation 7 never
+    m1, v1, _, _ = handle.gp_cv(f, y, info, offsets, dup, MARGINAL)
+    keep = np.arange(n) != 7
+    assert_close(m1[keep], m0[keep], 1e-12, "duplicate index: the other observations")
+    assert m1[7] == 0.0 and v1[7] == 0.0
 
 
 # ---- exact GP (tests/test_gp.cc, tests/lib/albatross/test/test_models.cc) -----------------------
@@ -215,8 +282,8 @@ def test_large_fit_residual_and_consistency(handle):
     _, offsets, indices = capi.group_indexers(np.arange(n))
     m, v, _, _ = handle.gp_cv(f, y, info, offsets, indices, MARGINAL)
     Kinv_diag = np.diag(np.linalg.inv(K))
-    assert_close(v, 1.0 / Kinv_diag, 1e-8)
-    assert_close(m, y - info / Kinv_diag, 1e-8)
+    assert_close(v, 1.0 / Kinv_diag, 1e-9, "LOO variance vs dense algebra")
+    assert_close(m, y - info / Kinv_diag, 1e-9, "LOO mean vs dense algebra")
 
 
 @pytest.mark.parametrize("n", [4096, 4097, 6000])

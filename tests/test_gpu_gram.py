@@ -72,6 +72,19 @@ def test_radial_edge_cases(handle, op):
     assert np.all(handle.gram_sym([op], [-2.0, sigma], x).download() == 0.0)
 
 
+@pytest.mark.parametrize("op", [SE, EXP, M32, M52])
+def test_nan_length_scale_propagates(handle, op):
+    """radial.hpp:28-30 tests `length_scale <= 0.`, which is false for NaN: a corrupt hyper-parameter must
+    surface as NaN covariances (and then as a not-positive-definite fit), never as a silent zero."""
+    x = features(130, 3, 12)
+    k = handle.gram_sym([op], [np.nan, 1.3], x).download()
+    assert np.all(np.isnan(k))
+    want = Restate.gram_sym([op], [np.nan, 1.3], x)
+    assert np.all(np.isnan(want))
+    k = handle.gram_sym([op, NOISE, SUM], [np.nan, 1.3, 0.1, 0, 0, 0], x[:, :1]).download()
+    assert np.all(np.isnan(k))
+
+
 def test_noise_is_value_equality(handle):
     """noise.hpp:37-43: duplicated features get off-diagonal noise; all coordinates must match."""
     x = features(70, 3, 5)
