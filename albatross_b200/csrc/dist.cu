@@ -187,6 +187,43 @@ int64_t dist_total(ab_handle_s *h, int64_t local) {
 
 namespace {
 
+// Launch helpers issue on h->stream; the panel chain borrows it for a scope.
+struct StreamSwap {
+  StreamSwap(ab_handle_s *h, cudaStream_t s) : h_(h), saved_(h->stream) { h->stream = s; }
+  ~StreamSwap() { h_->stream = saved_; }
+  ab_handle_s *h_;
+  cudaStream_t saved_;
+};
+
+// Per-step timing events of the distributed factorisation (grown on demand, owned by the process).
+struct DistEvents {
+  std::vector<cudaEvent_t> wait_begin, wait_end, panel_begin, panel_end;
+  cudaEvent_t factor_end = nullptr;
+  int64_t steps = 0;
+};
+
+DistEvents &dist_events(ab_handle_s *h, int64_t nblk) {
+  static std::map<ab_handle_s *, DistEvents> table;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  DistEvents &ev = table[h];
+  if (ev.factor_end == nullptr) {
+    cudaEventCreate(&ev.factor_end);
+  }
+  while (static_cast<int64_t>(ev.wait_begin.size()) < nblk) {
+    cudaEvent_t e[4];
+    for (auto &x : e) {
+      cudaEventCreate(&x);
+    }
+    ev.wait_begin.push_back(e[0]);
+    ev.wait_end.push_back(e[1]);
+    ev.panel_begin.push_back(e[2]);
+    ev.panel_end.push_back(e[3]);
+  }
+  ev.steps = nblk;
+  return ev;
+}
+
 // The distributed fit proper.  F: dim x n device features (replicated); d_y, d_yvar: device vectors.
 int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const double *d_y,
                   const double *d_yvar, int64_t n, int64_t nb, ab_dist_factor_s *fac,
@@ -228,7 +265,14 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   phase_end(h, PH_GRAM);
 
   // ---- factorisation --------------------------------------------------------------------------
+  // Three streams per rank: S (h->stream) runs the trailing updates, PS (high priority) the panel chain of
+  // the block column this rank owns next — leaf factorisations and small GEMMs that use 1-2 % of the SMs —
+  // and CS (high priority) the broadcasts.  Look-ahead 1: at step k the owner of block column k+1 updates
+  // that column first (on S), then factors and packs it on PS while S goes on with the rest of update k,
+  // so that neither the panel chain nor the broadcast is ever on the critical path of the DMMA work.
   phase_begin(h, PH_FACTOR);
+  AB_TRY(ensure_panel_stream(h));
+  cudaStream_t S = h->stream, PS = h->panel_stream, CS = h->comm_stream;
   const int64_t ldp_max = round_up(n, 2);
   void *pb[2] = {nullptr, nullptr};
   const size_t pbytes = static_cast<size_t>(ldp_max) * static_cast<size_t>(nb) * sizeof(double);
@@ -238,66 +282,81 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   AB_TRY(sc.alloc(static_cast<size_t>(nblk) * sizeof(int), &d_bad));
   {
     std::vector<int> init(static_cast<size_t>(nblk), INT_MAX);
-    AB_CUDA(cudaMemcpyAsync(d_bad, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice,
-                            h->stream));
-    AB_CUDA(cudaStreamSynchronize(h->stream)); // `init` is a stack temporary
+    AB_CUDA(cudaMemcpyAsync(d_bad, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice, S));
+    AB_CUDA(cudaStreamSynchronize(S)); // `init` is a stack temporary
   }
+  // accounting (ab_dist_fit_breakdown): time S spends waiting for a panel, time of the panel chains
+  DistEvents &ev = dist_events(h, nblk);
   auto panel = [&](int64_t k) {
     return MatView{static_cast<double *>(pb[k % 2]), round_up(n - k * nb, 2)};
   };
-  // owner only: factor block column k (diagonal potrf + TRSM of the rows below) and pack it
+  // owner only, on PS: factor block column k (diagonal potrf + TRSM of the rows below) and pack it
   auto factor_and_pack = [&](int64_t k) -> int {
+    StreamSwap swap(h, PS);
     const int64_t r0 = k * nb, wk = width(k), hk = n - r0;
     const MatView D = colblk(k).sub(r0, 0);
+    AB_CUDA(cudaEventRecord(ev.panel_begin[k], PS));
     AB_TRY(potrf(h, D, wk, dinv_of(k), static_cast<int *>(d_bad) + k));
     AB_TRY(trsm_right_lower_T(h, D, dinv_of(k), wk, D.sub(wk, 0), hk - wk));
     const MatView Pk = panel(k);
     AB_CUDA(cudaMemcpy2DAsync(Pk.p, Pk.ld * sizeof(double), D.p, D.ld * sizeof(double),
                               static_cast<size_t>(hk) * sizeof(double), static_cast<size_t>(wk),
-                              cudaMemcpyDeviceToDevice, h->stream));
+                              cudaMemcpyDeviceToDevice, PS));
+    AB_CUDA(cudaEventRecord(ev.panel_end[k], PS));
     return AB_OK;
   };
-  // A[j*nb:, block j] -= L[j*nb:, block k] L[block j rows, block k]^T   (j > k, j owned by me)
+  // A[j*nb:, block j] -= L[j*nb:, block k] L[block j rows, block k]^T   (j > k, j owned by me): the
+  // diagonal block as a DSYRK (lower tiles only), the rows below it as one tall DGEMM
   auto update = [&](int64_t j, int64_t k) -> int {
     const MatView Pk = panel(k);
-    const int64_t off = (j - k) * nb;
-    return gemm(h, GEMM_TRANS_B, n - j * nb, width(j), width(k), -1., Pk.sub(off, 0),
-                Pk.sub(off, 0), 1., colblk(j).sub(j * nb, 0));
-  };
-  auto bcast = [&](int64_t k) -> int {
-    if (W == 1) {
-      return AB_OK;
+    const int64_t off = (j - k) * nb, wj = width(j), wk = width(k), rows = n - j * nb;
+    const MatView C = colblk(j).sub(j * nb, 0);
+    AB_TRY(gemm(h, GEMM_TRANS_B | GEMM_LOWER, wj, wj, wk, -1., Pk.sub(off, 0), Pk.sub(off, 0), 1., C));
+    if (rows > wj) {
+      AB_TRY(gemm(h, GEMM_TRANS_B, rows - wj, wj, wk, -1., Pk.sub(off + wj, 0), Pk.sub(off, 0), 1.,
+                  C.sub(wj, 0)));
     }
+    return AB_OK;
+  };
+  // enqueue the broadcast of panel k on CS; afterwards ev_bcast[k % 2] says "panel k is in pb[k % 2]"
+  auto bcast = [&](int64_t k) -> int {
     const MatView Pk = panel(k);
     const int root = static_cast<int>(k % W);
     if (root == me) {
-      AB_CUDA(cudaEventRecord(h->ev_ready, h->stream));
-      AB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+      AB_CUDA(cudaStreamWaitEvent(CS, ev.panel_end[k], 0));
     } else {
-      // the buffer was last read by the updates of step k-2, all enqueued on h->stream by now
-      AB_CUDA(cudaEventRecord(h->ev_free, h->stream));
-      AB_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_free, 0));
+      // the buffer was last read by the updates of step k-2, all enqueued on S by now
+      AB_CUDA(cudaEventRecord(h->ev_free, S));
+      AB_CUDA(cudaStreamWaitEvent(CS, h->ev_free, 0));
     }
-    AB_NCCL(g_nccl.Broadcast(Pk.p, Pk.p, static_cast<size_t>(Pk.ld * width(k)), ncclDouble, root,
-                             comm_of(h), h->comm_stream));
-    AB_CUDA(cudaEventRecord(h->ev_bcast[k % 2], h->comm_stream));
+    if (W > 1) {
+      AB_NCCL(g_nccl.Broadcast(Pk.p, Pk.p, static_cast<size_t>(Pk.ld * width(k)), ncclDouble, root,
+                               comm_of(h), CS));
+    }
+    AB_CUDA(cudaEventRecord(h->ev_bcast[k % 2], CS));
     return AB_OK;
   };
 
   if (nblk > 0) {
     if (me == 0) {
+      // PS starts behind the Gram build on S
+      AB_CUDA(cudaEventRecord(h->ev_ready, S));
+      AB_CUDA(cudaStreamWaitEvent(PS, h->ev_ready, 0));
       AB_TRY(factor_and_pack(0));
     }
     AB_TRY(bcast(0));
   }
   for (int64_t k = 0; k < nblk; ++k) {
-    if (W > 1) {
-      AB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_bcast[k % 2], 0)); // panel k has arrived
-    }
+    AB_CUDA(cudaEventRecord(ev.wait_begin[k], S));
+    AB_CUDA(cudaStreamWaitEvent(S, h->ev_bcast[k % 2], 0)); // panel k has arrived
+    AB_CUDA(cudaEventRecord(ev.wait_end[k], S));
     const int64_t next = k + 1;
     if (next < nblk) {
       if (next % W == me) {
         AB_TRY(update(next, k));
+        // PS: behind this update (and with it behind every earlier reader of pb[next % 2])
+        AB_CUDA(cudaEventRecord(h->ev_ready, S));
+        AB_CUDA(cudaStreamWaitEvent(PS, h->ev_ready, 0));
         AB_TRY(factor_and_pack(next));
       }
       AB_TRY(bcast(next));
@@ -309,39 +368,64 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
       AB_TRY(update(j, k));
     }
   }
+  // S continues (the solves read every block column) only after the last panel chain
+  if (nblk > 0 && (nblk - 1) % W == me) {
+    AB_CUDA(cudaStreamWaitEvent(S, ev.panel_end[nblk - 1], 0));
+  }
+  AB_CUDA(cudaEventRecord(ev.factor_end, S));
   phase_end(h, PH_FACTOR);
 
   // ---- information = K^-1 y by block substitution ----------------------------------------------
+  // Left-looking in both directions, so that every step is one short-and-fat matrix-vector product that ALL
+  // ranks perform concurrently on their own block columns (the row-block slice of L they own), one tiny
+  // collective and one 1024 x 1024 block solve on the owner:
+  //   forward   z_j = L_jj^-1 (y_j - sum_r p_r),  p_r = L[block j rows, rank r's columns < j] z[those columns]
+  //   backward  x_j = L_jj^-T (z_j - t_j),  then every rank: t[own columns < j] += L[block j rows, .]^T x_j
+  // (round 1 was right-looking: the owner of block j streamed its whole panel below the diagonal inside
+  // step j, so the 69 GB of L at N = 131 072 were read one GPU at a time: 180 ms on 2, 4 and 8 GPUs alike.)
   phase_begin(h, PH_SOLVE);
   const size_t nbytes = static_cast<size_t>(round_up(n, 2)) * sizeof(double);
-  void *d_u = nullptr, *d_z = nullptr, *d_t = nullptr, *d_logs = nullptr;
-  AB_TRY(sc.alloc(nbytes, &d_u));
+  const int64_t nloc1 = std::max<int64_t>(nloc, 1);
+  const size_t lbytes = static_cast<size_t>(nloc1 * nb) * sizeof(double);
+  void *d_z = nullptr, *d_zl = nullptr, *d_tl = nullptr, *d_p = nullptr, *d_t = nullptr, *d_logs = nullptr;
   AB_TRY(sc.alloc(nbytes, &d_z));
+  AB_TRY(sc.alloc(lbytes, &d_zl));
+  AB_TRY(sc.alloc(lbytes, &d_tl));
+  AB_TRY(sc.alloc(static_cast<size_t>(nb) * sizeof(double), &d_p));
   AB_TRY(sc.alloc(static_cast<size_t>(nb) * sizeof(double), &d_t));
   AB_TRY(sc.alloc(static_cast<size_t>(nblk) * sizeof(double), &d_logs));
-  AB_CUDA(cudaMemsetAsync(d_u, 0, nbytes, h->stream));
   AB_CUDA(cudaMemsetAsync(d_z, 0, nbytes, h->stream));
+  AB_CUDA(cudaMemsetAsync(d_zl, 0, lbytes, h->stream));
+  AB_CUDA(cudaMemsetAsync(d_tl, 0, lbytes, h->stream));
   AB_CUDA(cudaMemsetAsync(d_logs, 0, static_cast<size_t>(nblk) * sizeof(double), h->stream));
-  double *u = static_cast<double *>(d_u), *z = static_cast<double *>(d_z);
+  double *z = static_cast<double *>(d_z), *zl = static_cast<double *>(d_zl);
+  double *tl = static_cast<double *>(d_tl), *pbuf = static_cast<double *>(d_p);
   double *t = static_cast<double *>(d_t);
-  const int64_t ldv = round_up(n, 2);
-  // forward: z_k = L_kk^-1 (y_k - sum_r u_r[k]),  u_me[below] += L[below, k] z_k
-  for (int64_t k = 0; k < nblk; ++k) {
-    const int64_t r0 = k * nb, wk = width(k), hk = n - r0;
-    const int root = static_cast<int>(k % W);
+  // number of this rank's block columns with global index < j
+  auto owned_before = [&](int64_t j) { return j > me ? (j - me + W - 1) / W : int64_t(0); };
+  for (int64_t j = 0; j < nblk; ++j) {
+    const int64_t r0 = j * nb, wj = width(j);
+    const int root = static_cast<int>(j % W);
+    const int64_t kcols = owned_before(j) * nb;
+    if (kcols > 0) {
+      AB_TRY(gemv_n(h, wj, kcols, 1., A.sub(r0, 0), zl, 0., pbuf));
+    } else {
+      AB_CUDA(cudaMemsetAsync(pbuf, 0, static_cast<size_t>(wj) * sizeof(double), h->stream));
+    }
     if (W > 1) {
-      AB_NCCL(g_nccl.Reduce(u + r0, t, static_cast<size_t>(wk), ncclDouble, ncclSum, root,
-                            comm_of(h), h->stream));
+      AB_NCCL(g_nccl.Reduce(pbuf, t, static_cast<size_t>(wj), ncclDouble, ncclSum, root, comm_of(h),
+                            h->stream));
     }
     if (root == me) {
-      sub_kernel<<<static_cast<unsigned>((wk + 255) / 256), 256, 0, h->stream>>>(
-          d_y + r0, W > 1 ? t : u + r0, wk, z + r0);
+      double *zj = zl + (j / W) * nb;
+      sub_kernel<<<static_cast<unsigned>((wj + 255) / 256), 256, 0, h->stream>>>(
+          d_y + r0, W > 1 ? t : pbuf, wj, zj);
       AB_LAUNCHED(h);
-      const MatView D = colblk(k).sub(r0, 0);
-      AB_TRY(trsm_left_lower(h, D, dinv_of(k), wk, MatView{z + r0, ldv}, 1));
-      AB_TRY(gemm(h, 0u, hk - wk, 1, wk, 1., D.sub(wk, 0), MatView{z + r0, ldv}, 1.,
-                  MatView{u + r0 + wk, ldv}));
-      AB_TRY(logdet_chol(h, D, wk, static_cast<double *>(d_logs) + k));
+      const MatView D = colblk(j).sub(r0, 0);
+      AB_TRY(trsv_block(h, false, D, dinv_of(j), wj, zj));
+      AB_CUDA(cudaMemcpyAsync(z + r0, zj, static_cast<size_t>(wj) * sizeof(double),
+                              cudaMemcpyDeviceToDevice, h->stream));
+      AB_TRY(logdet_chol(h, D, wj, static_cast<double *>(d_logs) + j));
     }
   }
   // [0] = |z|^2 (own blocks; others are zero), [1] = sum of own log-determinants
@@ -349,22 +433,24 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
                                                        h->d_scalars + 8);
   AB_LAUNCHED(h);
   AB_TRY(dist_allreduce_sum(h, h->d_scalars + 8, 2));
-  // backward: x_k = L_kk^-T (z_k - L[below, k]^T x[below]), broadcast x_k
   double *x = d_info;
-  for (int64_t k = nblk - 1; k >= 0; --k) {
-    const int64_t r0 = k * nb, wk = width(k), hk = n - r0;
-    const int root = static_cast<int>(k % W);
+  for (int64_t j = nblk - 1; j >= 0; --j) {
+    const int64_t r0 = j * nb, wj = width(j);
+    const int root = static_cast<int>(j % W);
     if (root == me) {
-      const MatView D = colblk(k).sub(r0, 0);
-      AB_CUDA(cudaMemcpyAsync(x + r0, z + r0, static_cast<size_t>(wk) * sizeof(double),
-                              cudaMemcpyDeviceToDevice, h->stream));
-      AB_TRY(gemm(h, GEMM_TRANS_A, wk, 1, hk - wk, -1., D.sub(wk, 0), MatView{x + r0 + wk, ldv}, 1.,
-                  MatView{x + r0, ldv}));
-      AB_TRY(trsm_left_lower_T(h, D, dinv_of(k), wk, MatView{x + r0, ldv}, 1));
+      const int64_t l = j / W;
+      sub_kernel<<<static_cast<unsigned>((wj + 255) / 256), 256, 0, h->stream>>>(
+          zl + l * nb, tl + l * nb, wj, x + r0);
+      AB_LAUNCHED(h);
+      AB_TRY(trsv_block(h, true, colblk(j).sub(r0, 0), dinv_of(j), wj, x + r0));
     }
     if (W > 1) {
-      AB_NCCL(g_nccl.Broadcast(x + r0, x + r0, static_cast<size_t>(wk), ncclDouble, root,
-                               comm_of(h), h->stream));
+      AB_NCCL(g_nccl.Broadcast(x + r0, x + r0, static_cast<size_t>(wj), ncclDouble, root, comm_of(h),
+                               h->stream));
+    }
+    const int64_t kcols = owned_before(j) * nb;
+    if (kcols > 0) {
+      AB_TRY(gemv_t(h, wj, kcols, 1., A.sub(r0, 0), x + r0, 1., tl));
     }
   }
   phase_end(h, PH_SOLVE);

@@ -404,7 +404,7 @@ constexpr int GEMV_WARPS = 8;
 // c[m] = alpha * A[m x k] b[k] + beta * c ; A column-major.  CTA = 32 rows; warp w walks the columns
 // kk = w, w + 8, ...; lane = row (256 contiguous bytes per warp load); deterministic reduction.
 __global__ void __launch_bounds__(GEMV_ROWS *GEMV_WARPS)
-gemv_n_kernel(int64_t m, int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
+gemv_n_unaligned_kernel(int64_t m, int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
               const double *__restrict__ b, double beta, double *c) {
   __shared__ double red[GEMV_WARPS][GEMV_ROWS];
   const int lane = threadIdx.x & 31;
@@ -442,7 +442,7 @@ gemv_n_kernel(int64_t m, int64_t k, double alpha, const double *__restrict__ A, 
 
 // c[m] = alpha * A^T b + beta * c ; A stored k x m (k contiguous).  One CTA per output element.
 __global__ void __launch_bounds__(256)
-gemv_t_kernel(int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
+gemv_t_unaligned_kernel(int64_t k, double alpha, const double *__restrict__ A, int64_t lda,
               const double *__restrict__ b, double beta, double *c) {
   __shared__ double red[8];
   const double *a = A + blockIdx.x * lda;
@@ -490,12 +490,15 @@ int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double
   }
   if (n == 1 && !tb && m > 1 && C.p != B.p && C.p != A.p && k > 0) {
     // B is a contiguous k-vector (op(B) = B, one column)
+    if (gemv_fast_ok(A, B.p)) { // 16-byte loads, k-split grids (trsv.cu)
+      return ta ? gemv_t(h, k, m, alpha, A, B.p, beta, C.p) : gemv_n(h, m, k, alpha, A, B.p, beta, C.p);
+    }
     if (ta) {
-      gemv_t_kernel<<<static_cast<unsigned>(m), 256, 0, h->stream>>>(k, alpha, A.p, A.ld, B.p,
+      gemv_t_unaligned_kernel<<<static_cast<unsigned>(m), 256, 0, h->stream>>>(k, alpha, A.p, A.ld, B.p,
                                                                       beta, C.p);
     } else {
       const unsigned blocks = static_cast<unsigned>((m + GEMV_ROWS - 1) / GEMV_ROWS);
-      gemv_n_kernel<<<blocks, GEMV_ROWS * GEMV_WARPS, 0, h->stream>>>(m, k, alpha, A.p, A.ld, B.p,
+      gemv_n_unaligned_kernel<<<blocks, GEMV_ROWS * GEMV_WARPS, 0, h->stream>>>(m, k, alpha, A.p, A.ld, B.p,
                                                                       beta, C.p);
     }
     AB_LAUNCHED(h);

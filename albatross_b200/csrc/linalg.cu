@@ -229,6 +229,9 @@ int trsm_left_lower(ab_handle_s *h, MatView L, const double *dinv, int64_t n, Ma
   if (n <= 0 || p <= 0) {
     return AB_OK;
   }
+  if (p == 1 && n > LEAF && gemv_fast_ok(L, X.p)) {
+    return trsv_lower(h, L, dinv, n, X.p); // one right-hand side: block substitution (trsv.cu)
+  }
   if (n <= LEAF) {
     return gemm(h, 0u, n, p, n, 1., leaf_inverse(dinv), X, 0., X);
   }
@@ -243,6 +246,9 @@ int trsm_left_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, 
                       int64_t p) {
   if (n <= 0 || p <= 0) {
     return AB_OK;
+  }
+  if (p == 1 && n > LEAF && gemv_fast_ok(L, X.p)) {
+    return trsv_lower_T(h, L, dinv, n, X.p);
   }
   if (n <= LEAF) {
     return gemm(h, GEMM_TRANS_A, n, p, n, 1., leaf_inverse(dinv), X, 0., X);

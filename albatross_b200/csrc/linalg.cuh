@@ -51,6 +51,20 @@ int trsm_right_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n,
 // (the strict upper triangle of an in-place factor holds stale data).  Y must not alias X.
 int trmm_left_lower(ab_handle_s *h, MatView L, int64_t n, bool trans, MatView X, MatView Y, int64_t p);
 
+// ---- one right-hand side (trsv.cu) --------------------------------------------------------------------
+// y[m] = beta y + alpha A[m x k] x[k] and y[k] = beta y + alpha A[m x k]^T x[m]; 16-byte loads: callers check
+// gemv_fast_ok (A 16-byte aligned with an even leading dimension, x 16-byte aligned).
+bool gemv_fast_ok(MatView A, const double *x);
+int gemv_n(ab_handle_s *h, int64_t m, int64_t k, double alpha, MatView A, const double *x, double beta,
+           double *y);
+int gemv_t(ab_handle_s *h, int64_t m, int64_t k, double alpha, MatView A, const double *x, double beta,
+           double *y);
+// One diagonal block of at most 1024 rows solved by one CTA: x <- L^-1 x or L^-T x.
+int trsv_block(ab_handle_s *h, bool trans, MatView L, const double *dinv, int64_t nb, double *x);
+// x <- L^-1 x, x <- L^-T x for a contiguous vector; L 16-byte aligned with an even leading dimension.
+int trsv_lower(ab_handle_s *h, MatView L, const double *dinv, int64_t n, double *x);
+int trsv_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, double *x);
+
 // out[0] = sum_i 2 log(L_ii)
 int logdet_chol(ab_handle_s *h, MatView L, int64_t n, double *d_out);
 // out[0] = sum_i a_i * b_i
