@@ -77,7 +77,7 @@ SYMBOLS = [
     "ab_sparse_predict2", "ab_factor_sqrt_product", "ab_factor_sqrt_transpose_solve",
     "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
-    "ab_dist_factor_free", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
+    "ab_dist_factor_free", "ab_dist_fit_breakdown", "ab_dist_factor_broadcast", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
     "ab_partition_triangular",
 ]
 DIST_ID_BYTES = 128
@@ -571,6 +571,18 @@ class Handle:
                                     C.c_int(x.shape[1]), _d(y), _d(yv), C.c_int64(nb),
                                     C.byref(out), _d(info), C.byref(nll)))
         return DistFactor(self, out), info, nll.value
+
+    def dist_factor_broadcast(self, factor, root=0):
+        """Rank `root` passes its Factor, the others None; every rank returns a Factor of the same L."""
+        ptr = C.c_void_p(factor.ptr.value if factor is not None else None)
+        _check(lib().ab_dist_factor_broadcast(self.ptr, C.byref(ptr), C.c_int(root)))
+        return factor if factor is not None else Factor(self, ptr)
+
+    def dist_fit_breakdown(self):
+        """(wait_ms, panel_ms, steps) of the most recent dist_gp_fit on this rank."""
+        w, p, n = C.c_double(), C.c_double(), C.c_int64()
+        _check(lib().ab_dist_fit_breakdown(self.ptr, C.byref(w), C.byref(p), C.byref(n)))
+        return w.value, p.value, n.value
 
     def dist_gram_rows(self, ops, params, feats):
         """This rank's row block of the symmetric Gram: returns (row0, Matrix[rows x n])."""

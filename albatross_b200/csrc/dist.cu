@@ -187,6 +187,22 @@ int64_t dist_total(ab_handle_s *h, int64_t local) {
 
 namespace {
 
+// The broadcast stream and the events that tie it to the update / panel streams (created on first use: a
+// world-1 group runs the same schedule without NCCL).
+int ensure_dist_streams(ab_handle_s *h) {
+  if (h->comm_stream != nullptr) {
+    return AB_OK;
+  }
+  int lo = 0, hi = 0;
+  AB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  AB_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+  AB_CUDA(cudaEventCreateWithFlags(&h->ev_bcast[0], cudaEventDisableTiming));
+  AB_CUDA(cudaEventCreateWithFlags(&h->ev_bcast[1], cudaEventDisableTiming));
+  AB_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+  AB_CUDA(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
+  return AB_OK;
+}
+
 // Launch helpers issue on h->stream; the panel chain borrows it for a scope.
 struct StreamSwap {
   StreamSwap(ab_handle_s *h, cudaStream_t s) : h_(h), saved_(h->stream) { h->stream = s; }
@@ -198,15 +214,22 @@ struct StreamSwap {
 // Per-step timing events of the distributed factorisation (grown on demand, owned by the process).
 struct DistEvents {
   std::vector<cudaEvent_t> wait_begin, wait_end, panel_begin, panel_end;
+  std::vector<char> owned; // panel k was factored by this rank in the most recent fit
   cudaEvent_t factor_end = nullptr;
   int64_t steps = 0;
 };
 
+std::map<ab_handle_s *, DistEvents> g_dist_events;
+std::mutex g_dist_events_mu;
+
+DistEvents &dist_events_existing(ab_handle_s *h) {
+  std::lock_guard<std::mutex> lock(g_dist_events_mu);
+  return g_dist_events[h];
+}
+
 DistEvents &dist_events(ab_handle_s *h, int64_t nblk) {
-  static std::map<ab_handle_s *, DistEvents> table;
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  DistEvents &ev = table[h];
+  std::lock_guard<std::mutex> lock(g_dist_events_mu);
+  DistEvents &ev = g_dist_events[h];
   if (ev.factor_end == nullptr) {
     cudaEventCreate(&ev.factor_end);
   }
@@ -221,6 +244,7 @@ DistEvents &dist_events(ab_handle_s *h, int64_t nblk) {
     ev.panel_end.push_back(e[3]);
   }
   ev.steps = nblk;
+  ev.owned.assign(static_cast<size_t>(nblk), 0);
   return ev;
 }
 
@@ -272,6 +296,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   // so that neither the panel chain nor the broadcast is ever on the critical path of the DMMA work.
   phase_begin(h, PH_FACTOR);
   AB_TRY(ensure_panel_stream(h));
+  AB_TRY(ensure_dist_streams(h));
   cudaStream_t S = h->stream, PS = h->panel_stream, CS = h->comm_stream;
   const int64_t ldp_max = round_up(n, 2);
   void *pb[2] = {nullptr, nullptr};
@@ -296,6 +321,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     const int64_t r0 = k * nb, wk = width(k), hk = n - r0;
     const MatView D = colblk(k).sub(r0, 0);
     AB_CUDA(cudaEventRecord(ev.panel_begin[k], PS));
+    ev.owned[static_cast<size_t>(k)] = 1;
     AB_TRY(potrf(h, D, wk, dinv_of(k), static_cast<int *>(d_bad) + k));
     AB_TRY(trsm_right_lower_T(h, D, dinv_of(k), wk, D.sub(wk, 0), hk - wk));
     const MatView Pk = panel(k);
@@ -521,14 +547,7 @@ int ab_dist_init(ab_handle h, int rank, int world, const void *id) {
   ncclComm_t comm = nullptr;
   AB_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
   h->comm = comm;
-  int lo = 0, hi = 0;
-  AB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  AB_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
-  AB_CUDA(cudaEventCreateWithFlags(&h->ev_bcast[0], cudaEventDisableTiming));
-  AB_CUDA(cudaEventCreateWithFlags(&h->ev_bcast[1], cudaEventDisableTiming));
-  AB_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
-  AB_CUDA(cudaEventCreateWithFlags(&h->ev_free, cudaEventDisableTiming));
-  return AB_OK;
+  return ensure_dist_streams(h);
 }
 
 int ab_dist_finalize(ab_handle h) {
@@ -536,15 +555,21 @@ int ab_dist_finalize(ab_handle h) {
   Lock lock(h);
   if (h->comm != nullptr) {
     cudaStreamSynchronize(h->stream);
-    cudaStreamSynchronize(h->comm_stream);
+    if (h->comm_stream != nullptr) {
+      cudaStreamSynchronize(h->comm_stream);
+    }
     g_nccl.CommDestroy(comm_of(h));
     h->comm = nullptr;
+  }
+  if (h->comm_stream != nullptr) { // also created by a world-1 ab_dist_gp_fit
+    cudaStreamSynchronize(h->comm_stream);
     cudaStreamDestroy(h->comm_stream);
     h->comm_stream = nullptr;
     cudaEventDestroy(h->ev_bcast[0]);
     cudaEventDestroy(h->ev_bcast[1]);
     cudaEventDestroy(h->ev_ready);
     cudaEventDestroy(h->ev_free);
+    h->ev_bcast[0] = h->ev_bcast[1] = h->ev_ready = h->ev_free = nullptr;
   }
   h->rank = 0;
   h->world = 1;
@@ -623,6 +648,35 @@ int ab_dist_gp_fit(ab_handle h, const ab_op *prog, int nops, const double *feats
   return s;
 }
 
+int ab_dist_fit_breakdown(ab_handle h, double *wait_ms, double *panel_ms, int64_t *steps) {
+  AB_REQUIRE(h != nullptr, "null handle");
+  Lock lock(h);
+  AB_CUDA(cudaStreamSynchronize(h->stream));
+  DistEvents &ev = dist_events_existing(h);
+  double w = 0., p = 0.;
+  for (int64_t k = 0; k < ev.steps; ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.wait_begin[k], ev.wait_end[k]) == cudaSuccess) {
+      w += ms;
+    }
+    if (ev.owned[static_cast<size_t>(k)] &&
+        cudaEventElapsedTime(&ms, ev.panel_begin[k], ev.panel_end[k]) == cudaSuccess) {
+      p += ms;
+    }
+  }
+  cudaGetLastError(); // events of a fit that never ran report an error: not ours to keep
+  if (wait_ms != nullptr) {
+    *wait_ms = w;
+  }
+  if (panel_ms != nullptr) {
+    *panel_ms = p;
+  }
+  if (steps != nullptr) {
+    *steps = ev.steps;
+  }
+  return AB_OK;
+}
+
 int ab_dist_factor_free(ab_handle h, ab_dist_factor f) {
   AB_REQUIRE(h != nullptr, "null handle");
   Lock lock(h);
@@ -664,6 +718,67 @@ int ab_dist_gram_rows(ab_handle h, const ab_op *prog, int nops, const double *fe
     *rows = nr;
   }
   *out = K;
+  return AB_OK;
+}
+
+int ab_dist_factor_broadcast(ab_handle h, ab_factor *factor, int root) {
+  AB_REQUIRE(h != nullptr && factor != nullptr, "null");
+  Lock lock(h);
+  AB_REQUIRE(root >= 0 && root < h->world, "root rank");
+  if (h->world <= 1) {
+    return AB_OK;
+  }
+  AB_REQUIRE(h->comm != nullptr, "distributed group not initialised");
+  const bool is_root = h->rank == root;
+  AB_REQUIRE(is_root ? *factor != nullptr : *factor == nullptr,
+             "the root passes its factor, every other rank a null handle");
+  // header: n and the first bad pivot (a factor that is not usable is replicated as such)
+  h->h_scalars[40] = is_root ? static_cast<double>((*factor)->n) : 0.;
+  h->h_scalars[41] = is_root ? static_cast<double>((*factor)->bad_pivot) : 0.;
+  AB_CUDA(cudaMemcpyAsync(h->d_scalars + 40, h->h_scalars + 40, 2 * sizeof(double),
+                          cudaMemcpyHostToDevice, h->stream));
+  AB_NCCL(g_nccl.Broadcast(h->d_scalars + 40, h->d_scalars + 40, 2, ncclDouble, root, comm_of(h),
+                           h->stream));
+  AB_TRY(download_bytes(h, h->d_scalars + 40, 2 * sizeof(double), h->h_scalars + 40));
+  const int64_t n = static_cast<int64_t>(h->h_scalars[40]);
+  ab_factor_s *f = is_root ? *factor : nullptr;
+  if (!is_root) {
+    ab_matrix_s *m = nullptr;
+    AB_TRY(matrix_new(h, n, n, &m));
+    int s = new_factor(h, m, &f);
+    if (s != AB_OK) {
+      matrix_delete(h, m);
+      return s;
+    }
+    f->bad_pivot = static_cast<int64_t>(h->h_scalars[41]);
+  }
+  // one broadcast of the factor matrix (identical leading dimension on every rank: padded_ld(n)) and one
+  // of the explicit leaf inverses
+  timings_reset(h);
+  phase_begin(h, PH_H2D);
+  int status = AB_OK;
+  if (n > 0) {
+    if (g_nccl.Broadcast(f->m->d, f->m->d, static_cast<size_t>(f->m->ld) * static_cast<size_t>(n),
+                         ncclDouble, root, comm_of(h), h->stream) != ncclSuccess ||
+        g_nccl.Broadcast(f->dinv, f->dinv, f->dinv_bytes / sizeof(double), ncclDouble, root, comm_of(h),
+                         h->stream) != ncclSuccess) {
+      set_error("ncclBroadcast of the factor failed");
+      status = AB_ERR_NCCL;
+    }
+  }
+  phase_end(h, PH_H2D);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess && status == AB_OK) {
+    set_error("factor broadcast failed");
+    status = AB_ERR_CUDA;
+  }
+  if (status != AB_OK) {
+    if (!is_root) {
+      delete_factor(h, f);
+    }
+    return status;
+  }
+  *factor = f;
   return AB_OK;
 }
 

@@ -364,7 +364,7 @@ constexpr int64_t LA_NB = AB_POTRF_NB; // panel width (multiple of LEAF)
 constexpr int64_t LA_MIN_N = 4 * LA_NB; // below this the plain recursion is used
 static_assert(LA_NB % LEAF == 0, "panel width");
 
-static int ensure_panel_stream(ab_handle_s *h) {
+int ensure_panel_stream(ab_handle_s *h) {
   if (h->panel_stream != nullptr) {
     return AB_OK;
   }

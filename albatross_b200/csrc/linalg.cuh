@@ -40,6 +40,9 @@ int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, dou
 // index of the first non-positive pivot (initialise to INT_MAX).
 int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad);
 
+// Creates (once) the handle's high-priority panel stream used by the look-ahead factorisations.
+int ensure_panel_stream(ab_handle_s *h);
+
 // X <- L^-1 X  (n x p), X <- L^-T X, X <- X L^-T (m x n, L n x n), using dinv for the leaves.
 int trsm_left_lower(ab_handle_s *h, MatView L, const double *dinv, int64_t n, MatView X, int64_t p);
 int trsm_left_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, MatView X,

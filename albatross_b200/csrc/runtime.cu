@@ -230,6 +230,13 @@ int ab_destroy(ab_handle h) {
   if (h->h_stage != nullptr) {
     cudaFreeHost(h->h_stage);
   }
+  if (h->comm_stream != nullptr) { // left by a world-1 distributed fit (ab_dist_finalize not called)
+    cudaStreamDestroy(h->comm_stream);
+    cudaEventDestroy(h->ev_bcast[0]);
+    cudaEventDestroy(h->ev_bcast[1]);
+    cudaEventDestroy(h->ev_ready);
+    cudaEventDestroy(h->ev_free);
+  }
   if (h->panel_stream != nullptr) {
     cudaStreamDestroy(h->panel_stream);
     cudaEventDestroy(h->ev_panel);

@@ -4,10 +4,11 @@
 // LDLT::_solve_impl (reference third_party/eigen/Eigen/src/Cholesky/LDLT.h:558-592) for a single column.
 // Round 1 ran them through the GEMM-shaped recursion of linalg.cu: ~4000 dependent single-CTA launches per
 // solve at N = 65 536 (41 ms for 34 GB of reads, 14 % of HBM peak in the GEMV that carried them).  Here a
-// solve is n / 1024 steps of two kernels:
-//   * trsv_block_kernel: one CTA solves a 1024 x 1024 diagonal block, the right-hand side living in shared
-//     memory; its 64 x 64 leaves are multiplications by the explicit leaf inverses the factorisation already
-//     produced (dinv), the rest of the block is streamed once;
+// solve is n / 512 steps of two kernels:
+//   * trsv_block_kernel: one CTA solves a diagonal block (512 rows on one GPU, the 1024-row block columns
+//     of the distributed factor), the right-hand side living in shared memory; its 64 x 64 leaves are
+//     multiplications by the explicit leaf inverses the factorisation already produced (dinv), the rest of
+//     the block is streamed once through a cp.async staging buffer;
 //   * gemv_n_kernel / gemv_t_kernel: the panel below the block times the solved segment (forward) or its
 //     transpose times the solved tail (backward), 16-byte loads, eight of them in flight per thread, k-split
 //     over the grid with a deterministic second-pass reduction when the matrix is short and fat.
@@ -18,23 +19,57 @@
 
 namespace ab {
 
-constexpr int TRSV_BLOCK = 1024; // diagonal block solved by one CTA (multiple of LEAF)
+constexpr int TRSV_BLOCK = 1024; // largest diagonal block one CTA solves (multiple of LEAF)
+// Block size of the single-GPU substitution loops: the in-block work of the lone CTA grows with the square
+// of the block, the number of (launch-latency bound) steps falls with it; 512 balances the two.
+constexpr int TRSV_STEP = 512;
 constexpr int TRSV_THREADS = 512;
 static_assert(TRSV_BLOCK % LEAF == 0, "block size");
 
 // Solves L x = b (TRANS == false) or L^T x = b (TRANS == true) for one diagonal block of `nb` <= 1024 rows,
 // in place in `x`.  L: the block's lower triangle (column-major, leading dimension ld); dinv: the explicit
 // inverses of its LEAF x LEAF diagonal leaves (identity-padded for a ragged last leaf).
+//
+// The CTA runs alone on one SM, so its speed is set by how many loads it keeps in flight.  Plain loads do
+// not work: ptxas interleaves them two by two with the FMAs that consume them (to save registers), the
+// in-order warps stall on every pair and the block streams at ~10 GB/s (measured: 41 ms per N = 65 536
+// solve).  The panel slice below / beside a leaf is therefore staged through shared memory with cp.async —
+// fire-and-forget copies, 32 per thread per chunk, all in flight at once — and consumed from there.
+constexpr int TRSV_CHUNK = 256;                     // rows per staged chunk
+constexpr int TRSV_STAGE = TRSV_CHUNK * LEAF;       // doubles: 128 KB
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// stage[c * TRSV_CHUNK + r] = L[row0 + r, col0 + c] for r < rows (<= TRSV_CHUNK), c < LEAF
+__device__ __forceinline__ void stage_chunk(double *stage, const double *__restrict__ L, int64_t ld,
+                                            int row0, int col0, int rows, int tid) {
+  for (int idx = tid; idx < TRSV_STAGE; idx += TRSV_THREADS) {
+    const int r = idx % TRSV_CHUNK;
+    const int c = idx / TRSV_CHUNK;
+    if (r < rows) {
+      cp_async8(stage + idx, L + (row0 + r) + static_cast<int64_t>(col0 + c) * ld);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+}
+
 template <bool TRANS>
 __global__ void __launch_bounds__(TRSV_THREADS)
 trsv_block_kernel(const double *__restrict__ L, int64_t ld, const double *__restrict__ dinv, int nb,
                   double *x) {
-  __shared__ double xs[TRSV_BLOCK];
-  __shared__ double ys[LEAF];
+  extern __shared__ __align__(16) double trsv_smem[];
+  double *stage = trsv_smem;              // TRSV_STAGE
+  double *xs = stage + TRSV_STAGE;        // TRSV_BLOCK
+  double *ys = xs + TRSV_BLOCK;           // LEAF
+  double *part = ys + LEAF;               // TRSV_THREADS
   const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  constexpr int NWARPS = TRSV_THREADS / 32;
   for (int i = tid; i < TRSV_BLOCK; i += TRSV_THREADS) {
     xs[i] = i < nb ? x[i] : 0.;
   }
@@ -44,64 +79,118 @@ trsv_block_kernel(const double *__restrict__ L, int64_t ld, const double *__rest
     for (int leaf = 0; leaf < nleaf; ++leaf) {
       const int c0 = leaf * LEAF;
       const double *inv = dinv + static_cast<int64_t>(leaf) * LEAF * LEAF;
-      // y = inv * xs[c0 .. c0 + 64): thread r < 64 owns row r (coalesced along r for every column)
+      // y = inv * xs[c0 .. c0 + 64): the 64 x 64 inverse goes through the stage as well
+      for (int idx = tid; idx < LEAF * LEAF; idx += TRSV_THREADS) {
+        cp_async8(stage + idx, inv + idx);
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      { // thread (r, q): row r, columns q * 8 .. q * 8 + 8 (8 partial sums per row)
+        const int r = tid & (LEAF - 1), q = tid >> 6;
+        double acc = 0.;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          acc = fma(stage[r + (q * 8 + c) * LEAF], xs[c0 + q * 8 + c], acc);
+        }
+        part[tid] = acc;
+      }
+      __syncthreads();
       if (tid < LEAF) {
         double acc = 0.;
-#pragma unroll 8
-        for (int c = 0; c < LEAF; ++c) {
-          acc = fma(inv[tid + c * LEAF], xs[c0 + c], acc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          acc += part[tid + q * LEAF];
         }
         ys[tid] = acc;
+        xs[c0 + tid] = acc;
       }
       __syncthreads();
-      if (tid < LEAF) {
-        xs[c0 + tid] = ys[tid];
-      }
-      // rows below the leaf inside the block: xs[r] -= L[r, c0 .. c0 + 64) . y
-      const int r0 = c0 + LEAF;
-      for (int r = r0 + tid; r < nb; r += TRSV_THREADS) {
-        const double *row = L + r + static_cast<int64_t>(c0) * ld;
-        double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-#pragma unroll 4
-        for (int c = 0; c < LEAF; c += 4) {
-          a0 = fma(row[static_cast<int64_t>(c) * ld], ys[c], a0);
-          a1 = fma(row[static_cast<int64_t>(c + 1) * ld], ys[c + 1], a1);
-          a2 = fma(row[static_cast<int64_t>(c + 2) * ld], ys[c + 2], a2);
-          a3 = fma(row[static_cast<int64_t>(c + 3) * ld], ys[c + 3], a3);
+      // rows below the leaf inside the block: xs[r] -= L[r, c0 .. c0 + 64) . y, TRSV_CHUNK rows at a time
+      for (int r0 = c0 + LEAF; r0 < nb; r0 += TRSV_CHUNK) {
+        const int rows = min(TRSV_CHUNK, nb - r0);
+        stage_chunk(stage, L, ld, r0, c0, rows, tid);
+        const int r = tid % TRSV_CHUNK, hlf = tid / TRSV_CHUNK; // two threads per row, 32 columns each
+        double a0 = 0., a1 = 0.;
+        if (r < rows) {
+#pragma unroll
+          for (int c = 0; c < LEAF / 2; c += 2) {
+            const int cc = hlf * (LEAF / 2) + c;
+            a0 = fma(stage[cc * TRSV_CHUNK + r], ys[cc], a0);
+            a1 = fma(stage[(cc + 1) * TRSV_CHUNK + r], ys[cc + 1], a1);
+          }
         }
-        xs[r] -= (a0 + a1) + (a2 + a3);
+        part[tid] = a0 + a1;
+        __syncthreads();
+        if (tid < rows) {
+          xs[r0 + tid] -= part[tid] + part[tid + TRSV_CHUNK];
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
   } else {
     for (int leaf = nleaf - 1; leaf >= 0; --leaf) {
       const int c0 = leaf * LEAF;
-      const int r0 = c0 + LEAF;
       const double *inv = dinv + static_cast<int64_t>(leaf) * LEAF * LEAF;
-      // t[c] = sum_{r >= r0} L[r, c0 + c] xs[r]: one warp per column (contiguous rows), 4 columns per warp
-      for (int c = warp; c < LEAF; c += NWARPS) {
-        const double *col = L + static_cast<int64_t>(c0 + c) * ld;
-        double acc = 0.;
-        for (int r = r0 + lane; r < nb; r += 32) {
-          acc = fma(col[r], xs[r], acc);
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        }
-        if (lane == 0) {
-          ys[c] = xs[c0 + c] - acc;
-        }
+      // t[c] = sum_{r >= c0 + 64} L[r, c0 + c] xs[r], accumulated chunk by chunk in ys (starting at 0)
+      if (tid < LEAF) {
+        ys[tid] = 0.;
       }
       __syncthreads();
-      // x_leaf = inv^T ys: thread c owns column c of inv (contiguous)
-      if (tid < LEAF) {
-        const double *col = inv + tid * LEAF;
-        double acc = 0.;
-#pragma unroll 8
-        for (int r = 0; r < LEAF; ++r) {
-          acc = fma(col[r], ys[r], acc);
+      for (int r0 = c0 + LEAF; r0 < nb; r0 += TRSV_CHUNK) {
+        const int rows = min(TRSV_CHUNK, nb - r0);
+        stage_chunk(stage, L, ld, r0, c0, rows, tid);
+        // a warp owns 4 columns; its lanes walk 32 consecutive rows at a time (conflict-free), then reduce
+        const int lane = tid & 31, warp = tid >> 5;
+        double acc[4] = {0., 0., 0., 0.};
+#pragma unroll
+        for (int g = 0; g < TRSV_CHUNK / 32; ++g) {
+          const int rr = g * 32 + lane;
+          const bool in = rr < rows; // rows beyond the chunk hold stale staging data
+          const double xv = in ? xs[r0 + rr] : 0.;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const double lv = in ? stage[(warp * 4 + qq) * TRSV_CHUNK + rr] : 0.;
+            acc[qq] = fma(lv, xv, acc[qq]);
+          }
         }
-        xs[c0 + tid] = acc;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          double t = acc[qq];
+          for (int o = 16; o > 0; o >>= 1) {
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+          }
+          if (lane == 0) {
+            ys[warp * 4 + qq] += t;
+          }
+        }
+        __syncthreads();
+      }
+      // x_leaf = inv^T (xs_leaf - t): thread (c, q): column c of inv (contiguous), rows q * 8 .. q * 8 + 8
+      for (int idx = tid; idx < LEAF * LEAF; idx += TRSV_THREADS) {
+        cp_async8(stage + idx, inv + idx);
+      }
+      cp_async_wait_all();
+      if (tid < LEAF) {
+        ys[tid] = xs[c0 + tid] - ys[tid];
+      }
+      __syncthreads();
+      {
+        const int q = tid & 7, c = tid >> 3;
+        double acc = 0.;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc = fma(stage[c * LEAF + q * 8 + i], ys[q * 8 + i], acc);
+        }
+        part[tid] = acc;
+      }
+      __syncthreads();
+      if (tid < LEAF) {
+        double total = 0.;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          total += part[tid * 8 + g];
+        }
+        xs[c0 + tid] = total;
       }
       __syncthreads();
     }
@@ -110,6 +199,8 @@ trsv_block_kernel(const double *__restrict__ L, int64_t ld, const double *__rest
     x[i] = xs[i];
   }
 }
+
+constexpr size_t TRSV_SMEM = (TRSV_STAGE + TRSV_BLOCK + LEAF + TRSV_THREADS) * sizeof(double);
 
 // ---- y[m] = beta y + alpha A[m x k] x[k] ---------------------------------------------------------------
 // CTA = 8 warps as WR x WC: a warp covers 64 consecutive rows with one 16-byte load per lane and column,
@@ -366,19 +457,29 @@ int trsv_block(ab_handle_s *h, bool trans, MatView L, const double *dinv, int64_
     return AB_OK;
   }
   AB_REQUIRE(nb <= TRSV_BLOCK, "trsv block too large");
+  static bool configured = false;
+  if (!configured) {
+    AB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(TRSV_SMEM)));
+    AB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(TRSV_SMEM)));
+    configured = true;
+  }
   if (trans) {
-    trsv_block_kernel<true><<<1, TRSV_THREADS, 0, h->stream>>>(L.p, L.ld, dinv, static_cast<int>(nb), x);
+    trsv_block_kernel<true><<<1, TRSV_THREADS, TRSV_SMEM, h->stream>>>(L.p, L.ld, dinv,
+                                                                        static_cast<int>(nb), x);
   } else {
-    trsv_block_kernel<false><<<1, TRSV_THREADS, 0, h->stream>>>(L.p, L.ld, dinv, static_cast<int>(nb), x);
+    trsv_block_kernel<false><<<1, TRSV_THREADS, TRSV_SMEM, h->stream>>>(L.p, L.ld, dinv,
+                                                                         static_cast<int>(nb), x);
   }
   AB_LAUNCHED(h);
   return AB_OK;
 }
 
-// x <- L^-1 x: right-looking over 1024-row blocks.
+// x <- L^-1 x: right-looking over TRSV_STEP-row blocks.
 int trsv_lower(ab_handle_s *h, MatView L, const double *dinv, int64_t n, double *x) {
-  for (int64_t k0 = 0; k0 < n; k0 += TRSV_BLOCK) {
-    const int64_t w = std::min<int64_t>(TRSV_BLOCK, n - k0);
+  for (int64_t k0 = 0; k0 < n; k0 += TRSV_STEP) {
+    const int64_t w = std::min<int64_t>(TRSV_STEP, n - k0);
     AB_TRY(trsv_block(h, false, L.sub(k0, k0), dinv + (k0 / LEAF) * LEAF * LEAF, w, x + k0));
     const int64_t below = n - k0 - w;
     if (below > 0) {
@@ -393,8 +494,8 @@ int trsv_lower_T(ab_handle_s *h, MatView L, const double *dinv, int64_t n, doubl
   if (n <= 0) {
     return AB_OK;
   }
-  for (int64_t k0 = (n - 1) / TRSV_BLOCK * TRSV_BLOCK; k0 >= 0; k0 -= TRSV_BLOCK) {
-    const int64_t w = std::min<int64_t>(TRSV_BLOCK, n - k0);
+  for (int64_t k0 = (n - 1) / TRSV_STEP * TRSV_STEP; k0 >= 0; k0 -= TRSV_STEP) {
+    const int64_t w = std::min<int64_t>(TRSV_STEP, n - k0);
     const int64_t below = n - k0 - w;
     if (below > 0) {
       AB_TRY(gemv_t(h, below, w, -1., L.sub(k0 + w, k0), x + k0 + w, 1., x + k0));

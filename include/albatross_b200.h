@@ -387,6 +387,13 @@ AB_API int ab_dist_gp_fit(ab_handle h, const ab_op *prog, int nops, const double
                    int dim, const double *y, const double *yvar, int64_t nb, ab_dist_factor *factor,
                    double *information, double *nll);
 AB_API int ab_dist_factor_free(ab_handle h, ab_dist_factor f);
+/*
+ * Where the most recent ab_dist_gp_fit on this rank spent its factorisation phase, from CUDA events on the
+ * update stream: wait_ms = time the trailing updates stood waiting for a panel broadcast (summed over the
+ * `steps` block columns), panel_ms = time of the panel chains this rank ran (diagonal factorisation + TRSM +
+ * packing, overlapped with the updates).  The rest of ab_timings().factor_ms is DSYRK / DGEMM work.
+ */
+AB_API int ab_dist_fit_breakdown(ab_handle h, double *wait_ms, double *panel_ms, int64_t *steps);
 /* Owner rank of block column j and its local index: the integer contract of the layout. */
 AB_API int ab_dist_block_owner(int64_t block, int world, int *rank, int64_t *local_block);
 /*
@@ -396,8 +403,17 @@ AB_API int ab_dist_block_owner(int64_t block, int world, int *rank, int64_t *loc
 AB_API int ab_dist_gram_rows(ab_handle h, const ab_op *prog, int nops, const double *feats, int64_t n,
                       int dim, int64_t *row0, int64_t *rows, ab_matrix *out);
 /*
+ * Replicates a single-GPU factor (ab_gp_fit / ab_potrf on rank `root`) onto every rank with one
+ * ncclBroadcast of L over NVLink (at N = 32 768 the factor is 8.6 GB, a few tens of
+ * milliseconds, against eight redundant 0.4 s factorisations).  The root passes its factor, which stays
+ * valid; every other rank passes a null handle and receives a new factor that it frees itself.
+ * ab_timings().h2d_ms reports the transfer.
+ */
+AB_API int ab_dist_factor_broadcast(ab_handle h, ab_factor *factor, int root);
+/*
  * Leave-one-group-out CV with folds sharded over ranks: every rank holds the same
- * single-GPU factor (N <= 65 536 fits one GPU); rank r processes groups g with g % world == r and
+ * single-GPU factor (N <= 65 536 fits one GPU; fit once and ab_dist_factor_broadcast it); rank r processes
+ * groups g with g % world == r and
  * the per-observation results are all-reduced.  Outputs as ab_gp_cv (joint blocks are returned only
  * for the caller's own groups, others zero-filled).
  */

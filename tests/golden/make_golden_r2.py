@@ -65,7 +65,63 @@ def section_sparse_mo(out):
     out["sptoy_var"] = Ref.sparse_gp(10, p, x, y, u, 0, 0.0, test=t, what=1)["var"]
 
 
-SECTIONS = {"sparse_mo": section_sparse_mo}
+def section_ldlt(out):
+    """What the reference's diagonally pivoted LDLT does with a singular positive SEMI-definite matrix:
+    duplicate points without a noise term (LDLT.h:316-338 pivots, :568-585 pseudo-inverse of D)."""
+    x = np.array([0.0, 1.0, 2.0, 2.0, 3.0, 1.0, 4.5, 0.0])
+    A = Ref.gram_sym(0, [1.0, 1.0], x)           # SE(1, 1), rank 5 of 8
+    rhs = np.sin(x)                               # in the range of A (equal rows carry equal values)
+    l = Ref.ldlt(A, rhs=rhs)
+    out["psd_x"], out["psd_A"], out["psd_rhs"] = x, A, rhs
+    out["psd_D"], out["psd_transpositions"] = l["D"], l["transpositions"]
+    out["psd_solve"] = l["solve"].ravel()
+    out["psd_logdet"] = np.array(l["logdet"])
+    out["psd_is_pd"] = np.array(int(l["is_pd"]))
+    out["psd_nll"] = np.array(Ref.gp_nll(6, [1.0, 1.0, 0.0], x, rhs)[0])  # SE + IndependentNoise(0)
+
+
+def section_sparse_nested(out):
+    """The nested sub-problem of BASELINE configs[4] the reference can still run (about 90 s per fit on one
+    core): N = 131 072 bench-shaped observations, M = 512 uniformly spaced inducing points, FITC and PITC
+    with 1024-point groups.  Inputs come from numpy's PCG64 (seed 0): only checksums are stored."""
+    n, m = 131072, 512
+    x = np.random.default_rng(0).uniform(0.0, 10.0, size=n)
+    y = np.sin(x) + 0.1 * np.cos(10.0 * x)
+    u = np.linspace(x.min(), x.max(), m)
+    t = np.linspace(0.0, 10.0, 64)
+    out["spn_n_m"] = np.array([n, m])
+    out["spn_x_checksum"] = np.array([x.sum(), x[12345], y.sum()])
+    out["spn_test"] = t
+    for tag, gk, ga in (("fitc", 0, 0.0), ("pitc", 2, n / 10.0 / 1024.0)):
+        r = Ref.sparse_gp(6, [1.0, 1.0, 0.1], x, y, u, gk, ga, test=t, what=1, want_ll=True)
+        out[f"spn_{tag}_mean"], out[f"spn_{tag}_var"] = r["mean"], r["var"]
+        out[f"spn_{tag}_ll"] = np.array(r["ll"])
+        print("  sparse_nested", tag, "ll", r["ll"], flush=True)
+
+
+def section_big(out):
+    """Exact GP at N = 8192 (3-D, SE(1, 1) + IndependentNoise(0.1)): the smallest size at which the device
+    factorisation takes its default look-ahead schedule.  Each reference pass is ~45 s of single-core LDLT."""
+    n = 8192
+    x = np.random.default_rng(8192).uniform(0.0, 10.0, size=(n, 3))
+    y = np.sin(x[:, 0]) + 0.1 * np.cos(10.0 * x[:, 0])
+    t = np.random.default_rng(1).uniform(0.0, 10.0, size=(48, 3))
+    p = [1.0, 1.0, 0.1]
+    out["big_x_checksum"] = np.array([x.sum(), x[4321, 1], y.sum()])
+    out["big_test"] = t
+    out["big_information"] = Ref.gp_fit(6, p, x, y)["information"]
+    print("  big: fit done", flush=True)
+    out["big_nll"] = np.array(Ref.gp_nll(6, p, x, y)[0])
+    mean, _, cov = Ref.gp_predict(6, p, x, y, t, 2)
+    out["big_mean"], out["big_cov"] = mean, cov
+    out["big_var"] = Ref.gp_predict(6, p, x, y, t, 1)[1]
+    print("  big: predictions done", flush=True)
+    m, v, _, s = Ref.gp_cv(6, p, x, y, 0, 0.0, what=1, want_score=True)
+    out["big_loo_mean"], out["big_loo_var"], out["big_loo_score"] = m, v, np.array(s)
+
+
+SECTIONS = {"sparse_mo": section_sparse_mo, "ldlt": section_ldlt, "sparse_nested": section_sparse_nested,
+            "big": section_big}
 
 
 def main():

@@ -248,4 +248,7 @@ def test_eigen_typed_build_matches_stand_in_types(dumped, tmp_path):
     for key, val in dumped.items():
         if key == "kernel_launches":
             continue
-        assert np.array_equal(val, e[key], equal_nan=True), key
+        # device results are bit-identical; scalars the layer reduces on the host (sums of per-group
+        # scores) may differ in the last bits with Eigen's summation order
+        assert val.shape == e[key].shape, key
+        assert np.allclose(val, e[key], rtol=1e-13, atol=0.0, equal_nan=True), key

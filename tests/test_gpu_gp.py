@@ -316,3 +316,66 @@ def test_lookahead_factorisation_matches_recursion(handle, n, monkeypatch):
     Kb[n - 3, n - 3] = -1.0
     fb = handle.potrf(handle.upload(Kb), allow_not_pd=True)
     assert not fb.is_positive_definite() and fb.info() == n - 3
+
+
+# ---- the default look-ahead schedule against the reference itself ------------------------------------
+
+def test_gp_n8192_default_schedule_vs_reference_fixture(handle, golden):
+    """N = 8192 is the smallest size at which ab_potrf takes its default schedule (look-ahead on two streams,
+    TMA-fed DSYRK); information / NLL / predictions / leave-one-out against outputs of the compiled reference
+    (tests/golden/make_golden_r2.py `big`, ~5 min of single-core Eigen LDLT) at the north_star 1e-9."""
+    _, ref = golden
+    n = 8192
+    x = np.random.default_rng(8192).uniform(0.0, 10.0, size=(n, 3))
+    y = np.sin(x[:, 0]) + 0.1 * np.cos(10.0 * x[:, 0])
+    assert np.array_equal(np.array([x.sum(), x[4321, 1], y.sum()]), ref["big_x_checksum"]), "RNG stream changed"
+    t = ref["big_test"]
+    ops, pp = prog(6)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    assert_close(info, ref["big_information"], RTOL, "information N=8192")
+    nll = handle.gp_nll(ops, pp, x, y)
+    assert abs(nll - float(ref["big_nll"])) <= RTOL * abs(float(ref["big_nll"])), (nll, float(ref["big_nll"]))
+    mean, var, _ = handle.gp_predict(f, ops, pp, x, info, t, MARGINAL)
+    assert_close(mean, ref["big_mean"], RTOL, "mean N=8192")
+    assert np.max(np.abs(var - ref["big_var"])) <= RTOL * 1.01, "marginal variance (prior scale 1.01)"
+    _, _, cov = handle.gp_predict(f, ops, pp, x, info, t, JOINT)
+    assert np.max(np.abs(cov - ref["big_cov"])) <= RTOL * 1.01, "joint covariance"
+    _, offsets, indices = capi.group_indexers(np.arange(n))
+    m, v, _, s = handle.gp_cv(f, y, info, offsets, indices, MARGINAL, want_score=True)
+    assert_close(m, ref["big_loo_mean"], RTOL, "LOO mean N=8192")
+    assert_close(v, ref["big_loo_var"], RTOL, "LOO variance N=8192")
+    assert abs(s - float(ref["big_loo_score"])) <= RTOL * abs(float(ref["big_loo_score"]))
+    f.free()
+
+
+def test_singular_psd_policy_next_to_the_reference(handle, golden):
+    """Duplicate points without a noise term: K is positive SEMI-definite (rank 5 of 8).
+    Reference (fixture from the compiled reference): the diagonally pivoted LDLT finishes with exact zeros in D
+    (LDLT.h:316-338), is_positive_definite() is false, log_determinant() is -inf and the log-likelihood NaN;
+    solve() goes through the pseudo-inverse of D (:568-585) and, for a right-hand side in the range of K,
+    returns an exact solution.
+    Device (policy): the unpivoted factorisation stops at the first non-positive pivot and
+    reports it (AB_ERR_NOT_PD, ab_factor_info); the factor is not usable for solves.  The trait layer turns
+    that into NaN outputs and is_positive_definite() == false, so likelihood-driven tuning sees what it sees
+    with the reference (NaN -> +inf objective, tune.hpp:164-166); only solve() on a consistent singular
+    system differs (NaN instead of a pseudo-inverse solution)."""
+    _, ref = golden
+    A, rhs = ref["psd_A"], ref["psd_rhs"]
+    # what the reference does
+    assert int(ref["psd_is_pd"]) == 0 and np.isneginf(float(ref["psd_logdet"])) and np.isnan(float(ref["psd_nll"]))
+    assert np.sum(ref["psd_D"] == 0.0) == 3
+    assert np.max(np.abs(A @ ref["psd_solve"] - rhs)) <= 1e-15
+    # what the device does
+    f = handle.potrf(handle.upload(A), allow_not_pd=True)
+    assert not f.is_positive_definite()
+    assert f.info() == 3            # x[3] duplicates x[2]: the first pivot that is not positive
+    with pytest.raises(capi.AbError) as err:
+        f.solve(rhs)
+    assert err.value.status == 4    # AB_ERR_NOT_PD
+    with pytest.raises(capi.AbError) as err:
+        handle.gp_nll([capi.SE], [1.0, 1.0], ref["psd_x"], rhs)
+    assert err.value.status == 4
+    # a noise term (the case every shipped model has) makes the same data positive definite on both sides
+    ops, pp = prog(6)
+    want = Restate.gp_nll(ops, pp, ref["psd_x"], rhs)
+    assert abs(handle.gp_nll(ops, pp, ref["psd_x"], rhs) - want) <= RTOL * abs(want)

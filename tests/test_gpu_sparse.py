@@ -213,7 +213,8 @@ def test_sparse_measurement_only_vs_oracle(handle, n, m, gk, ga):
     mean, _, cov = f.predict(*plain, t, JOINT)
     assert_close(mean, want["mean"], 1e-9, "mean")
     assert abs(ll - want["ll"]) <= 1e-9 * abs(want["ll"]), (ll, want["ll"])
-    assert np.max(np.abs(cov - want["cov"])) <= 1e-9 * np.max(np.abs(want["cov"]))
+    # the posterior covariance is prior - Q** + S** (sparse_gp.hpp:509-536): its error scales with the prior
+    assert np.max(np.abs(cov - want["cov"])) <= 1e-9 * P10[1] ** 2
     _, offsets, indices = capi.group_indexers(keys)
     assert_close(handle.sparse_log_likelihood(ops, pp, x, y, u, offsets, indices, fu=plain, uu=plain),
                  ll, 1e-12)

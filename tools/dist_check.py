@@ -84,8 +84,8 @@ def main():
         m1, v1, _, s1 = h.gp_cv(fc, yc, infoc, offsets, indices, MARGINAL, want_score=True)
         m2, v2, s2 = h.dist_gp_cv(fc, yc, infoc, offsets, indices, MARGINAL, want_score=True)
         report(f"cv {name} mean", rel(m2, m1), 1e-9)
-        report(f"cv {name} var", rel(v2, v1), 1e-8)
-        report(f"cv {name} score", abs(s2 - s1) / abs(s1), 1e-8)
+        report(f"cv {name} var", rel(v2, v1), 1e-9)
+        report(f"cv {name} score", abs(s2 - s1) / abs(s1), 1e-9)
     fc.free()
 
     # 4. sharded sparse GP: each rank passes its groups; result replicated
@@ -100,7 +100,7 @@ def main():
         sf, v, ll = h.sparse_fit(ops6, pp6, xl, yl, u, lo, li)
         mean, var, _ = sf.predict(ops6, pp6, tt, MARGINAL)
         report(f"sparse {name} mean", rel(mean, want["mean"]), 1e-9)
-        report(f"sparse {name} var", rel(var, want["var"]), 1e-8)
+        report(f"sparse {name} var", rel(var, want["var"]), 1e-9)
         report(f"sparse {name} ll", abs(ll - want["ll"]) / abs(want["ll"]), 1e-9)
         sf.free()
 
