@@ -331,16 +331,41 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     AB_CUDA(cudaEventRecord(ev.panel_end[k], PS));
     return AB_OK;
   };
-  // A[j*nb:, block j] -= L[j*nb:, block k] L[block j rows, block k]^T   (j > k, j owned by me): the
-  // diagonal block as a DSYRK (lower tiles only), the rows below it as one tall DGEMM
+  // A[j*nb:, block j] -= L[j*nb:, block k] L[block j rows, block k]^T   (j > k, j owned by me).
+  // One column at a time (the look-ahead column, and the fallback for shapes the TMA kernel does not take):
   auto update = [&](int64_t j, int64_t k) -> int {
     const MatView Pk = panel(k);
-    const int64_t off = (j - k) * nb, wj = width(j), wk = width(k), rows = n - j * nb;
-    const MatView C = colblk(j).sub(j * nb, 0);
-    AB_TRY(gemm(h, GEMM_TRANS_B | GEMM_LOWER, wj, wj, wk, -1., Pk.sub(off, 0), Pk.sub(off, 0), 1., C));
-    if (rows > wj) {
-      AB_TRY(gemm(h, GEMM_TRANS_B, rows - wj, wj, wk, -1., Pk.sub(off + wj, 0), Pk.sub(off, 0), 1.,
-                  C.sub(wj, 0)));
+    const int64_t off = (j - k) * nb;
+    return gemm(h, GEMM_TRANS_B, n - j * nb, width(j), width(k), -1., Pk.sub(off, 0), Pk.sub(off, 0), 1.,
+                colblk(j).sub(j * nb, 0));
+  };
+  // ... and ALL owned block columns j >= jfirst (jfirst owned by me) in ONE launch: they are contiguous in
+  // the local matrix, their B operands are the row blocks jfirst-k, jfirst-k+W, ... of the packed panel
+  // (CyclicB), and tiles above the stretched diagonal are skipped.  Per-column launches cost a partial last
+  // wave each (measured at N = 65 536 on 2 GPUs: 0.87 of the 1-GPU rate, 214 ms of tails in 1.6 s; the
+  // launches of one step carry 1/W of a full trailing update, so the loss grows with W).
+  auto update_from = [&](int64_t jfirst, int64_t k) -> int {
+    if (jfirst >= nblk) {
+      return AB_OK;
+    }
+    const MatView Pk = panel(k);
+    const int64_t R0 = jfirst * nb, m = n - R0, l0 = jfirst / W;
+    const int64_t jlast = me + (nloc - 1) * W;
+    const int64_t ncols = (nloc - 1 - l0) * nb + width(jlast);
+    CyclicB cyc;
+    cyc.blk = nb;
+    cyc.stride = static_cast<int64_t>(W) * nb;
+    cyc.row0 = (jfirst - k) * nb;
+    cyc.rows = n - k * nb;
+    int st = AB_ERR_UNSUPPORTED;
+    if (gemm_tma_enabled() && width(k) == nb) {
+      st = gemm_nt_tma(h, true, m, ncols, nb, -1., Pk.sub(R0 - k * nb, 0), Pk, 1., A.sub(R0, l0 * nb), &cyc);
+    }
+    if (st != AB_ERR_UNSUPPORTED) {
+      return st;
+    }
+    for (int64_t j = jfirst; j < nblk; j += W) {
+      AB_TRY(update(j, k));
     }
     return AB_OK;
   };
@@ -387,12 +412,12 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
       }
       AB_TRY(bcast(next));
     }
-    for (int64_t j = k + 1; j < nblk; ++j) {
-      if (j % W != me || (j == next && next % W == me)) {
-        continue; // not mine, or already updated ahead of the panel factorisation above
-      }
-      AB_TRY(update(j, k));
+    // my first block column after k that is still to be updated (the look-ahead column already is)
+    int64_t jfirst = k + 1 + ((me - (k + 1)) % W + W) % W;
+    if (jfirst == next && next % W == me) {
+      jfirst += W;
     }
+    AB_TRY(update_from(jfirst, k));
   }
   // S continues (the solves read every block column) only after the last panel chain
   if (nblk > 0 && (nblk - 1) % W == me) {

@@ -90,13 +90,18 @@ __device__ __forceinline__ unsigned swz(int r, int kk) {
 __global__ void __launch_bounds__(TTHREADS, 2)
 gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    int64_t m, int64_t n, int64_t k, double alpha, double beta, double *C, int64_t ldc,
-                   int tiles_m, int lower, int vec_ok) {
+                   int tiles_m, int lower, int vec_ok, int cyc_blk, int64_t cyc_stride, int64_t b_row0) {
   extern __shared__ __align__(1024) unsigned char tsmem[];
   __shared__ __align__(8) unsigned long long bars[2 * TSTAGES]; // full[0..S), empty[S..2S)
 
   const int64_t m0 = static_cast<int64_t>(blockIdx.x % tiles_m) * TBM;
   const int64_t n0 = static_cast<int64_t>(blockIdx.x / tiles_m) * TBN;
-  if (lower && m0 + TBM <= n0) {
+  // Block-cyclic B (CyclicB, linalg.cuh): column block q = n0 / cyc_blk of C multiplies the rows
+  // b_row0 + q * cyc_stride + (n0 % cyc_blk) ... of B, and "lower" is measured against that stretched
+  // diagonal.  cyc_blk == 0: the plain product (row n0 of B, the ordinary diagonal).
+  const int64_t gcol = cyc_blk > 0 ? (n0 / cyc_blk) * cyc_stride + (n0 % cyc_blk) : n0;
+  const int64_t brow = b_row0 + gcol;
+  if (lower && m0 + TBM <= gcol) {
     return; // strictly above the diagonal (whole CTA exits before any barrier is initialised)
   }
   const int tid = threadIdx.x;
@@ -133,7 +138,7 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
 #pragma unroll
     for (int b = 0; b < B_BOXES; ++b) {
-      tma_box(stage + (A_BOXES + b) * BOX_BYTES, &mapB, static_cast<int>(n0) + b * BOX_ROWS, kt * TBK,
+      tma_box(stage + (A_BOXES + b) * BOX_BYTES, &mapB, static_cast<int>(brow) + b * BOX_ROWS, kt * TBK,
               full);
     }
   };
@@ -298,7 +303,7 @@ bool gemm_tma_enabled() {
 // Returns AB_OK when the product was launched, AB_ERR_UNSUPPORTED when the caller must use the
 // cp.async kernel (shape / alignment outside what the tensor maps can describe).
 int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, double alpha, MatView A,
-                MatView B, double beta, MatView C) {
+                MatView B, double beta, MatView C, const CyclicB *cyc) {
   const auto aligned16 = [](const MatView &M) {
     return reinterpret_cast<uintptr_t>(M.p) % 16 == 0 && M.ld % 2 == 0;
   };
@@ -306,8 +311,13 @@ int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, dou
       n >= (int64_t(1) << 31) || k >= (int64_t(1) << 31) || C.p == A.p || C.p == B.p) {
     return AB_ERR_UNSUPPORTED;
   }
+  const bool cyclic = cyc != nullptr && cyc->blk > 0;
+  if (cyclic && (cyc->blk % TBN != 0 || cyc->rows >= (int64_t(1) << 31) || cyc->blk >= (int64_t(1) << 31))) {
+    return AB_ERR_UNSUPPORTED;
+  }
   CUtensorMap mapA, mapB;
-  if (!make_map(&mapA, A, m, k) || !make_map(&mapB, B, n, k)) {
+  // cyclic: B is the whole packed panel (cyc->rows rows); rows past its end read as zero (TMA fill)
+  if (!make_map(&mapA, A, m, k) || !make_map(&mapB, B, cyclic ? cyc->rows : n, k)) {
     return AB_ERR_UNSUPPORTED;
   }
   constexpr size_t smem = static_cast<size_t>(TSTAGES) * STAGE_BYTES + 1024; // + alignment slack
@@ -322,7 +332,8 @@ int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, dou
   AB_REQUIRE(tm * tn < (int64_t(1) << 31), "GEMM grid too large");
   const int vec_ok = aligned16(C) ? 1 : 0;
   gemm_nt_tma_kernel<<<static_cast<unsigned>(tm * tn), TTHREADS, smem, h->stream>>>(
-      mapA, mapB, m, n, k, alpha, beta, C.p, C.ld, static_cast<int>(tm), lower ? 1 : 0, vec_ok);
+      mapA, mapB, m, n, k, alpha, beta, C.p, C.ld, static_cast<int>(tm), lower ? 1 : 0, vec_ok,
+      cyclic ? static_cast<int>(cyc->blk) : 0, cyclic ? cyc->stride : 0, cyclic ? cyc->row0 : 0);
   AB_LAUNCHED(h);
   return AB_OK;
 }

@@ -31,8 +31,18 @@ int gemm(ab_handle_s *h, unsigned flags, int64_t m, int64_t n, int64_t k, double
 // TMA-fed kernel of the C = alpha A B^T + beta C product (gemm_tma.cu; on unless AB_GEMM_TMA=0).
 // AB_ERR_UNSUPPORTED = shape / alignment it does not cover: use the cp.async kernel.
 bool gemm_tma_enabled();
+// Block-cyclic B operand (the one-launch trailing update of the distributed factorisation, dist.cu): column
+// block q (width blk, a multiple of 64) of C multiplies rows row0 + q * stride + [0, blk) of B, which has
+// `rows` rows in all; with lower == true a tile is skipped when it lies entirely above that stretched
+// diagonal (its last row < row index q * stride + c of its first column).
+struct CyclicB {
+  int64_t blk = 0;
+  int64_t stride = 0;
+  int64_t row0 = 0;
+  int64_t rows = 0;
+};
 int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, double alpha, MatView A,
-                MatView B, double beta, MatView C);
+                MatView B, double beta, MatView C, const CyclicB *cyc = nullptr);
 
 // Blocked Cholesky of the lower triangle of the n x n matrix A, in place.  dinv receives the
 // explicit inverses of the LEAF x LEAF diagonal blocks of L (block j at dinv + j*LEAF*LEAF,

@@ -252,3 +252,17 @@ def test_eigen_typed_build_matches_stand_in_types(dumped, tmp_path):
         # scores) may differ in the last bits with Eigen's summation order
         assert val.shape == e[key].shape, key
         assert np.allclose(val, e[key], rtol=1e-13, atol=0.0, equal_nan=True), key
+
+
+def test_route_1b_real_reference_with_device_ldlt():
+    """INTEGRATION.md route 1b, executed: tests/cpp/route1b_check.cc includes the REAL reference headers and
+    instantiates the reference's own Fit<GPFit<CovarianceRepresentation, X>> (src/models/gp.hpp:42-78) and its
+    generic _predict_impl (:305-366) with albatross_b200::DeviceLDLT; the binary compares every output with the
+    stock SerializableLDLT model in-process at 1e-9."""
+    exe = os.path.join(ROOT, "tests", "cpp", "route1b_check")
+    if not os.path.exists(exe):
+        pytest.fail("tests/cpp/route1b_check missing: run __graft_entry__.build() where /root/reference exists")
+    res = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=900)
+    print(res.stdout)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "0 failure(s)" in res.stdout
