@@ -75,7 +75,7 @@ SYMBOLS = [
     "ab_sparse_fit", "ab_sparse_free", "ab_sparse_info", "ab_sparse_log_likelihood",
     "ab_sparse_predict", "ab_sparse_export_R", "ab_sparse_fit2", "ab_sparse_log_likelihood2",
     "ab_sparse_predict2", "ab_factor_sqrt_product", "ab_factor_sqrt_transpose_solve",
-    "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt",
+    "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt", "ab_qr_r",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
     "ab_dist_factor_free", "ab_dist_fit_breakdown", "ab_dist_factor_broadcast", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
     "ab_partition_triangular",
@@ -571,6 +571,14 @@ class Handle:
                                     C.c_int(x.shape[1]), _d(y), _d(yv), C.c_int64(nb),
                                     C.byref(out), _d(info), C.byref(nll)))
         return DistFactor(self, out), info, nll.value
+
+    def qr_r(self, B):
+        """R (upper triangular, P = I) of a thin QR of the host matrix B."""
+        Bf = np.asfortranarray(B, dtype=np.float64)
+        rows, cols = Bf.shape
+        R = np.empty((cols, cols), order="F")
+        _check(lib().ab_qr_r(self.ptr, _d(Bf), C.c_int64(rows), C.c_int64(cols), _d(R)))
+        return R
 
     def dist_factor_broadcast(self, factor, root=0):
         """Rank `root` passes its Factor, the others None; every rank returns a Factor of the same L."""

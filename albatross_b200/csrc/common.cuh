@@ -50,6 +50,23 @@ void set_error(const char *fmt, ...);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Kernel function attributes (the dynamic shared-memory opt-in) belong to a device, not to the process: one
+// process may drive several GPUs through several handles (the tuner's finite-difference evaluations,
+// include/albatross_b200/tune.hpp).  `static PerDeviceOnce once; if (once.need(h->device)) { ... }`.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need(int device) {
+    if (device < 0 || device >= 64) {
+      return true;
+    }
+    if (done[device]) {
+      return false;
+    }
+    done[device] = true;
+    return true;
+  }
+};
+
 // Leading dimension of a device matrix with `rows` rows: 16-double (128 B) aligned columns, and
 // never a multiple of 1024 doubles so that column walks do not alias in L2/HBM channels.
 inline int64_t padded_ld(int64_t rows) {

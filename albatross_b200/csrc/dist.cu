@@ -29,6 +29,7 @@
 #include <nccl.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 struct ab_dist_factor_s {
@@ -214,6 +215,7 @@ struct StreamSwap {
 // Per-step timing events of the distributed factorisation (grown on demand, owned by the process).
 struct DistEvents {
   std::vector<cudaEvent_t> wait_begin, wait_end, panel_begin, panel_end;
+  std::vector<cudaEvent_t> arrived, bulkdone, pdone; // per panel: broadcast landed / S done with it / PS done
   std::vector<char> owned; // panel k was factored by this rank in the most recent fit
   cudaEvent_t factor_end = nullptr;
   int64_t steps = 0;
@@ -242,6 +244,13 @@ DistEvents &dist_events(ab_handle_s *h, int64_t nblk) {
     ev.wait_end.push_back(e[1]);
     ev.panel_begin.push_back(e[2]);
     ev.panel_end.push_back(e[3]);
+    cudaEvent_t q[3];
+    for (auto &x : q) {
+      cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+    }
+    ev.arrived.push_back(q[0]);
+    ev.bulkdone.push_back(q[1]);
+    ev.pdone.push_back(q[2]);
   }
   ev.steps = nblk;
   ev.owned.assign(static_cast<size_t>(nblk), 0);
@@ -299,10 +308,24 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   AB_TRY(ensure_dist_streams(h));
   cudaStream_t S = h->stream, PS = h->panel_stream, CS = h->comm_stream;
   const int64_t ldp_max = round_up(n, 2);
-  void *pb[2] = {nullptr, nullptr};
+  // AB_DIST_SCHEDULE=lookahead1 selects the round-1 style schedule (two panel buffers, the owner of column
+  // k+1 prepares it inside step k on the update stream) for comparison; default: the decoupled pipeline
+  bool pipelined = true;
+  if (const char *e = std::getenv("AB_DIST_SCHEDULE")) {
+    pipelined = std::strcmp(e, "lookahead1") != 0;
+  }
+  int64_t NBUF = pipelined ? 4 : 2;
+  if (const char *e = std::getenv("AB_DIST_NBUF")) {
+    NBUF = std::max<int64_t>(2, std::min<int64_t>(16, std::atoll(e)));
+  }
+  if (!pipelined) {
+    NBUF = 2;
+  }
+  std::vector<void *> pb(static_cast<size_t>(NBUF), nullptr);
   const size_t pbytes = static_cast<size_t>(ldp_max) * static_cast<size_t>(nb) * sizeof(double);
-  AB_TRY(sc.alloc(pbytes, &pb[0]));
-  AB_TRY(sc.alloc(pbytes, &pb[1]));
+  for (auto &b : pb) {
+    AB_TRY(sc.alloc(pbytes, &b));
+  }
   void *d_bad = nullptr;
   AB_TRY(sc.alloc(static_cast<size_t>(nblk) * sizeof(int), &d_bad));
   {
@@ -313,7 +336,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   // accounting (ab_dist_fit_breakdown): time S spends waiting for a panel, time of the panel chains
   DistEvents &ev = dist_events(h, nblk);
   auto panel = [&](int64_t k) {
-    return MatView{static_cast<double *>(pb[k % 2]), round_up(n - k * nb, 2)};
+    return MatView{static_cast<double *>(pb[static_cast<size_t>(k % NBUF)]), round_up(n - k * nb, 2)};
   };
   // owner only, on PS: factor block column k (diagonal potrf + TRSM of the rows below) and pack it
   auto factor_and_pack = [&](int64_t k) -> int {
@@ -344,14 +367,16 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   // (CyclicB), and tiles above the stretched diagonal are skipped.  Per-column launches cost a partial last
   // wave each (measured at N = 65 536 on 2 GPUs: 0.87 of the 1-GPU rate, 214 ms of tails in 1.6 s; the
   // launches of one step carry 1/W of a full trailing update, so the loss grows with W).
-  auto update_from = [&](int64_t jfirst, int64_t k) -> int {
+  // count = -1: every owned column from jfirst on; count = 1: block column jfirst alone.
+  auto update_cols = [&](int64_t jfirst, int64_t count, int64_t k) -> int {
     if (jfirst >= nblk) {
       return AB_OK;
     }
     const MatView Pk = panel(k);
     const int64_t R0 = jfirst * nb, m = n - R0, l0 = jfirst / W;
-    const int64_t jlast = me + (nloc - 1) * W;
-    const int64_t ncols = (nloc - 1 - l0) * nb + width(jlast);
+    const int64_t llast = count < 0 ? nloc - 1 : std::min<int64_t>(l0 + count - 1, nloc - 1);
+    const int64_t jlast = me + llast * W;
+    const int64_t ncols = (llast - l0) * nb + width(jlast);
     CyclicB cyc;
     cyc.blk = nb;
     cyc.stride = static_cast<int64_t>(W) * nb;
@@ -364,11 +389,12 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     if (st != AB_ERR_UNSUPPORTED) {
       return st;
     }
-    for (int64_t j = jfirst; j < nblk; j += W) {
+    for (int64_t j = jfirst; j <= jlast; j += W) {
       AB_TRY(update(j, k));
     }
     return AB_OK;
   };
+  auto update_from = [&](int64_t jfirst, int64_t k) -> int { return update_cols(jfirst, -1, k); };
   // enqueue the broadcast of panel k on CS; afterwards ev_bcast[k % 2] says "panel k is in pb[k % 2]"
   auto bcast = [&](int64_t k) -> int {
     const MatView Pk = panel(k);
@@ -388,41 +414,124 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     return AB_OK;
   };
 
-  if (nblk > 0) {
-    if (me == 0) {
-      // PS starts behind the Gram build on S
-      AB_CUDA(cudaEventRecord(h->ev_ready, S));
+  if (pipelined) {
+    // ---- decoupled panel pipeline ---------------------------------------------------------------------
+    // The chain "apply panel k to the next column I own, factor it when it is complete, broadcast it" is
+    // sequential across the ranks and costs ~24 ms per step at N = 131 072 while a rank's share of the
+    // trailing update shrinks quadratically (43 ms at step 0 on 8 GPUs): from step ~56 of 128 on the chain,
+    // not the DMMA work, sets the pace (measured: 155 ms of 3.2 s waiting, profiles/r02g_*).  So the chain
+    // gets its own high-priority stream PS on every rank and never waits for the bulk: for every panel k,
+    // PS updates the first owned column after k (jstar) the moment the panel arrives and factors it as soon
+    // as it is complete, while S applies the panel to the owned columns beyond jstar in one launch.  S may
+    // lag up to NBUF - 1 panels behind (NBUF packed-panel buffers), which also lets ranks whose share of a
+    // step is one block column larger (4 % of the work at W = 8) drift instead of stalling the others.
+    std::vector<cudaEvent_t> &arrived = ev.arrived, &bulkdone = ev.bulkdone, &pdone = ev.pdone;
+    auto first_owned_after = [&](int64_t k) { return k + 1 + ((me - (k + 1)) % W + W) % W; };
+    // C stream: broadcast of panel k into buffer k % NBUF
+    auto bcast_p = [&](int64_t k) -> int {
+      const MatView Pk = panel(k);
+      const int root = static_cast<int>(k % W);
+      const int64_t prev = k - NBUF; // the panel this buffer held before
+      if (root == me) {
+        AB_CUDA(cudaStreamWaitEvent(CS, ev.panel_end[k], 0)); // packed (and with it: buffer was free)
+      } else if (prev >= 0) {
+        AB_CUDA(cudaStreamWaitEvent(CS, bulkdone[prev], 0));
+        AB_CUDA(cudaStreamWaitEvent(CS, pdone[prev], 0));
+      }
+      if (W > 1) {
+        AB_NCCL(g_nccl.Broadcast(Pk.p, Pk.p, static_cast<size_t>(Pk.ld * width(k)), ncclDouble, root,
+                                 comm_of(h), CS));
+      }
+      AB_CUDA(cudaEventRecord(arrived[k], CS));
+      return AB_OK;
+    };
+    // PS: factor + pack block column k (all its updates are on PS before this point)
+    auto factor_and_pack_p = [&](int64_t k) -> int {
+      const int64_t prev = k - NBUF;
+      if (prev >= 0) { // the pack overwrites buffer k % NBUF: its previous panel must be consumed
+        AB_CUDA(cudaStreamWaitEvent(PS, bulkdone[prev], 0)); // (PS's own use of it is stream-ordered)
+      }
+      return factor_and_pack(k);
+    };
+    if (nblk > 0) {
+      AB_CUDA(cudaEventRecord(h->ev_ready, S)); // PS starts behind the Gram build on S
       AB_CUDA(cudaStreamWaitEvent(PS, h->ev_ready, 0));
-      AB_TRY(factor_and_pack(0));
+      if (me == 0) {
+        AB_TRY(factor_and_pack_p(0));
+      }
+      AB_TRY(bcast_p(0));
     }
-    AB_TRY(bcast(0));
-  }
-  for (int64_t k = 0; k < nblk; ++k) {
-    AB_CUDA(cudaEventRecord(ev.wait_begin[k], S));
-    AB_CUDA(cudaStreamWaitEvent(S, h->ev_bcast[k % 2], 0)); // panel k has arrived
-    AB_CUDA(cudaEventRecord(ev.wait_end[k], S));
-    const int64_t next = k + 1;
-    if (next < nblk) {
-      if (next % W == me) {
-        AB_TRY(update(next, k));
-        // PS: behind this update (and with it behind every earlier reader of pb[next % 2])
+    for (int64_t k = 0; k < nblk; ++k) {
+      const int64_t jstar = first_owned_after(k);
+      // ---- PS: the next column I own
+      AB_CUDA(cudaStreamWaitEvent(PS, arrived[k], 0));
+      if (jstar < nblk) {
+        // S updated this column with the panels before my previous column (jstar - W); it must be done
+        // with them before PS takes the column over
+        const int64_t handover = jstar - W - 1;
+        if (k == std::max<int64_t>(jstar - W, 0) && handover >= 0) {
+          AB_CUDA(cudaStreamWaitEvent(PS, bulkdone[handover], 0));
+        }
+        {
+          StreamSwap swap(h, PS);
+          AB_TRY(update_cols(jstar, 1, k));
+        }
+      }
+      AB_CUDA(cudaEventRecord(pdone[k], PS));
+      if (jstar == k + 1 && jstar < nblk) {
+        AB_TRY(factor_and_pack_p(jstar));
+      }
+      // ---- S: everything I own beyond jstar
+      AB_CUDA(cudaEventRecord(ev.wait_begin[k], S));
+      AB_CUDA(cudaStreamWaitEvent(S, arrived[k], 0));
+      AB_CUDA(cudaEventRecord(ev.wait_end[k], S));
+      AB_TRY(update_cols(jstar + W, -1, k));
+      AB_CUDA(cudaEventRecord(bulkdone[k], S));
+      // ---- CS: the next panel
+      if (k + 1 < nblk) {
+        AB_TRY(bcast_p(k + 1));
+      }
+    }
+    // S continues (the solves read every block column) only after PS is done
+    AB_CUDA(cudaEventRecord(h->ev_ready, PS));
+    AB_CUDA(cudaStreamWaitEvent(S, h->ev_ready, 0));
+  } else {
+  if (nblk > 0) {
+      if (me == 0) {
+        // PS starts behind the Gram build on S
         AB_CUDA(cudaEventRecord(h->ev_ready, S));
         AB_CUDA(cudaStreamWaitEvent(PS, h->ev_ready, 0));
-        AB_TRY(factor_and_pack(next));
+        AB_TRY(factor_and_pack(0));
       }
-      AB_TRY(bcast(next));
+      AB_TRY(bcast(0));
     }
-    // my first block column after k that is still to be updated (the look-ahead column already is)
-    int64_t jfirst = k + 1 + ((me - (k + 1)) % W + W) % W;
-    if (jfirst == next && next % W == me) {
-      jfirst += W;
+    for (int64_t k = 0; k < nblk; ++k) {
+      AB_CUDA(cudaEventRecord(ev.wait_begin[k], S));
+      AB_CUDA(cudaStreamWaitEvent(S, h->ev_bcast[k % 2], 0)); // panel k has arrived
+      AB_CUDA(cudaEventRecord(ev.wait_end[k], S));
+      const int64_t next = k + 1;
+      if (next < nblk) {
+        if (next % W == me) {
+          AB_TRY(update(next, k));
+          // PS: behind this update (and with it behind every earlier reader of pb[next % 2])
+          AB_CUDA(cudaEventRecord(h->ev_ready, S));
+          AB_CUDA(cudaStreamWaitEvent(PS, h->ev_ready, 0));
+          AB_TRY(factor_and_pack(next));
+        }
+        AB_TRY(bcast(next));
+      }
+      // my first block column after k that is still to be updated (the look-ahead column already is)
+      int64_t jfirst = k + 1 + ((me - (k + 1)) % W + W) % W;
+      if (jfirst == next && next % W == me) {
+        jfirst += W;
+      }
+      AB_TRY(update_from(jfirst, k));
     }
-    AB_TRY(update_from(jfirst, k));
-  }
-  // S continues (the solves read every block column) only after the last panel chain
-  if (nblk > 0 && (nblk - 1) % W == me) {
-    AB_CUDA(cudaStreamWaitEvent(S, ev.panel_end[nblk - 1], 0));
-  }
+    // S continues (the solves read every block column) only after the last panel chain
+    if (nblk > 0 && (nblk - 1) % W == me) {
+      AB_CUDA(cudaStreamWaitEvent(S, ev.panel_end[nblk - 1], 0));
+    }
+}
   AB_CUDA(cudaEventRecord(ev.factor_end, S));
   phase_end(h, PH_FACTOR);
 

@@ -372,11 +372,10 @@ static int launch(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, d
   constexpr int A_ELEMS = tile_elems<BM, TA>();
   constexpr int B_ELEMS = tile_elems<BN, !TB>();
   constexpr size_t smem = static_cast<size_t>(STAGES) * (A_ELEMS + B_ELEMS) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need(h->device)) {
     AB_CUDA(cudaFuncSetAttribute(gemm_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-    configured = true;
   }
   const int64_t tm = (m + BM - 1) / BM;
   const int64_t tn = (n + BN - 1) / BN;

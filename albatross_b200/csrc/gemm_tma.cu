@@ -321,11 +321,10 @@ int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, dou
     return AB_ERR_UNSUPPORTED;
   }
   constexpr size_t smem = static_cast<size_t>(TSTAGES) * STAGE_BYTES + 1024; // + alignment slack
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need(h->device)) {
     AB_CUDA(cudaFuncSetAttribute(gemm_nt_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
-    configured = true;
   }
   const int64_t tm = (m + TBM - 1) / TBM;
   const int64_t tn = (n + TBN - 1) / TBN;

@@ -922,8 +922,8 @@ inline cudaError_t gram_launch(ab_handle_s *h, const DevProg &P, const double *f
                                int64_t n, const double *fy, int64_t ldfy, int64_t m, double *out,
                                int64_t ld, int tiles_i, unsigned ntiles, uint32_t flags) {
   constexpr size_t smem = gram_smem_bytes<DIM, SYM, EV>();
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
+  static PerDeviceOnce once;
+  if (smem > 48 * 1024 && once.need(h->device)) {
     cudaError_t e = cudaFuncSetAttribute(gram_kernel<DIM, SYM, EV, COLS, MINB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
@@ -938,7 +938,6 @@ inline cudaError_t gram_launch(ab_handle_s *h, const DevProg &P, const double *f
         return e;
       }
     }
-    configured = true;
   }
   const int64_t resident = static_cast<int64_t>(MINB) * h->sm_count;
   const unsigned grid = static_cast<unsigned>(ntiles < resident ? ntiles : resident);

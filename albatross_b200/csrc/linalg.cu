@@ -317,11 +317,10 @@ static int potrf_rec(ab_handle_s *h, MatView A, int64_t n, double *dinv, int64_t
                      int *d_bad) {
   if (n <= LEAF) {
     constexpr size_t smem = 2 * LEAF * LS * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need(h->device)) {
       AB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
-      configured = true;
     }
 #ifdef AB_LEAF_V1
     potf2_inv_kernel<<<1, 256, smem, h->stream>>>(A.p, A.ld, static_cast<int>(n), dinv, offset,

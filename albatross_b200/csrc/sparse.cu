@@ -626,6 +626,71 @@ int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int nops,
   return ab_sparse_predict2(h, f, prog, nops, prog, nops, test_feats, p, what, mean, var, cov);
 }
 
+// R of a thin QR of a dense host matrix (the QR concept of sparse_gp.hpp:72-89 for callers that build their
+// own B): CholQR2 on the device — S = B^T B, S = L1 L1^T, B <- B L1^-T, once more, R = (L1 L2)^T.
+int ab_qr_r(ab_handle h, const double *B, int64_t rows, int64_t cols, double *R) {
+  AB_REQUIRE(h != nullptr && B != nullptr && R != nullptr && rows >= cols && cols >= 1, "null / shape");
+  Lock lock(h);
+  Scope sc(h);
+  timings_reset(h);
+  ab_matrix_s *Bd = nullptr;
+  phase_begin(h, PH_H2D);
+  AB_TRY(upload(h, B, rows, cols, &Bd));
+  sc.own(Bd);
+  phase_end(h, PH_H2D);
+  phase_begin(h, PH_FACTOR);
+  ab_factor_s *L[2] = {nullptr, nullptr};
+  int status = AB_OK;
+  for (int pass = 0; pass < 2 && status == AB_OK; ++pass) {
+    ab_matrix_s *S = nullptr;
+    status = matrix_new(h, cols, cols, &S);
+    if (status != AB_OK) {
+      break;
+    }
+    status = gemm(h, GEMM_TRANS_A | GEMM_LOWER, cols, cols, rows, 1., view(Bd), view(Bd), 0., view(S));
+    if (status != AB_OK) {
+      matrix_delete(h, S);
+      break;
+    }
+    status = factorize(h, S, &L[pass]); // consumes S
+    if (status == AB_OK && pass == 0) {
+      status = trsm_right_lower_T(h, view(L[0]->m), L[0]->dinv, cols, view(Bd), rows);
+    }
+  }
+  phase_end(h, PH_FACTOR);
+  if (status == AB_OK) {
+    // R = (L1 L2)^T
+    ab_matrix_s *a = nullptr, *b = nullptr, *c = nullptr;
+    if ((status = matrix_new(h, cols, cols, &a)) == AB_OK) {
+      sc.own(a);
+    }
+    if (status == AB_OK && (status = matrix_new(h, cols, cols, &b)) == AB_OK) {
+      sc.own(b);
+    }
+    if (status == AB_OK && (status = matrix_new(h, cols, cols, &c)) == AB_OK) {
+      sc.own(c);
+    }
+    if (status == AB_OK) {
+      const dim3 g = grid2(cols, cols);
+      tril_copy_kernel<<<g, 256, 0, h->stream>>>(L[0]->m->d, L[0]->m->ld, cols, a->d, a->ld);
+      tril_copy_kernel<<<g, 256, 0, h->stream>>>(L[1]->m->d, L[1]->m->ld, cols, b->d, b->ld);
+      h->launches += 2;
+      status = gemm(h, 0u, cols, cols, cols, 1., view(a), view(b), 0., view(c));
+      if (status == AB_OK) {
+        transpose_kernel<<<g, 256, 0, h->stream>>>(c->d, c->ld, cols, a->d, a->ld);
+        h->launches++;
+        cudaEventRecord(h->ev_total_end, h->stream);
+        status = download(h, a, 0, 0, cols, cols, R);
+      }
+    }
+  } else if (status == AB_ERR_NOT_PD) {
+    set_error("ab_qr_r: B^T B is numerically singular (CholQR2 needs cond(B) below ~1e7)");
+  }
+  delete_factor(h, L[0]);
+  delete_factor(h, L[1]);
+  return status;
+}
+
 int ab_sparse_export_R(ab_handle h, ab_sparse f, double *R) {
   AB_REQUIRE(h != nullptr && f != nullptr && R != nullptr, "null");
   Lock lock(h);

@@ -457,13 +457,12 @@ int trsv_block(ab_handle_s *h, bool trans, MatView L, const double *dinv, int64_
     return AB_OK;
   }
   AB_REQUIRE(nb <= TRSV_BLOCK, "trsv block too large");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  if (once.need(h->device)) {
     AB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(TRSV_SMEM)));
     AB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(TRSV_SMEM)));
-    configured = true;
   }
   if (trans) {
     trsv_block_kernel<true><<<1, TRSV_THREADS, TRSV_SMEM, h->stream>>>(L.p, L.ld, dinv,

@@ -355,6 +355,14 @@ AB_API int ab_sparse_predict(ab_handle h, ab_sparse f, const ab_op *prog, int no
 AB_API int ab_sparse_predict2(ab_handle h, ab_sparse f, const ab_op *cross_prog, int cross_nops,
                        const ab_op *prior_prog, int prior_nops, const double *test_feats, int64_t p,
                        int what, double *mean, double *var, double *cov);
+/*
+ * R (cols x cols, upper triangular, column-major) of a thin QR of the dense host matrix B (rows x cols,
+ * rows >= cols): what QRImplementation::compute + get_R (sparse_gp.hpp:72-89, linalg/qr_utils.hpp:18-27)
+ * return, with P = I.  Computed as CholQR2 on the device (two passes of B^T B = L L^T, B <- B L^-T): valid
+ * for cond(B) below ~1e7, AB_ERR_NOT_PD beyond (the sparse model itself factors a better-conditioned
+ * matrix, see ab_sparse_fit).  R^T R = B^T B; the signs of R's diagonal are positive.
+ */
+AB_API int ab_qr_r(ab_handle h, const double *B, int64_t rows, int64_t cols, double *R);
 /* sigma_R (m x m upper triangular, column-major, get_R linalg/qr_utils.hpp:18-27) with P = I. */
 AB_API int ab_sparse_export_R(ab_handle h, ab_sparse f, double *R);
 

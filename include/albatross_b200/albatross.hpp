@@ -13,6 +13,7 @@
 #include "covariance.hpp"
 #include "device.hpp"
 #include "gp.hpp"
+#include "linalg.hpp"
 #include "linalg_types.hpp"
 #include "parameters.hpp"
 #include "sparse_gp.hpp"

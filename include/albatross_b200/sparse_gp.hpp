@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "gp.hpp"
+#include "linalg.hpp"
 
 namespace albatross_b200 {
 
@@ -31,9 +32,7 @@ struct UniformlySpacedInducingPoints { // sparse_gp.hpp:34-47
   std::size_t num_points;
 };
 
-// Marker with the reference's name; the factorisation behind it is the device CholQR2 (sparse.cu).
-struct DenseQRImplementation {};
-using DeviceQRImplementation = DenseQRImplementation;
+// DenseQRImplementation / DeviceQR / BlockDiagonalLDLT: linalg.hpp.
 
 template <typename InducingFeatureType> struct SparseGPFit {};
 

@@ -424,6 +424,56 @@ static void scenario_sparse_measurement_only() {
   dump("spmo.pitc.ll", pitc.log_likelihood(data) - pitc.prior_log_likelihood());
 }
 
+static void scenario_block_diagonal_and_qr() {
+  // BlockDiagonal(LDLT) (linalg/block_diagonal.hpp) and the QR concept (sparse_gp.hpp:72-89, qr_utils.hpp)
+  // exercised the way compute_internal_components / compute_sigma_qr use them (sparse_gp.hpp:368-375, :632-706)
+  auto data = make_1d(300, 21, 0., 10.);
+  auto cov = SE(1., 1.) + ab::IndependentNoise<double>(0.1);
+  ab::BlockDiagonal K_ff;
+  std::vector<std::size_t> sizes = {70, 1, 129, 100};
+  std::size_t at = 0;
+  for (std::size_t sz : sizes) {
+    std::vector<double> sub(data.features.begin() + at, data.features.begin() + at + sz);
+    K_ff.blocks.push_back(cov(ab::as_measurements(sub)));
+    at += sz;
+  }
+  const ab::BlockDiagonalLDLT A_ldlt = K_ff.ldlt();
+  EXPECT(A_ldlt.rows() == 300 && A_ldlt.is_positive_definite());
+  MatrixXd rhs(300, 2);
+  for (Index i = 0; i < 300; ++i) {
+    rhs(i, 0) = data.targets.mean[i];
+    rhs(i, 1) = std::cos(0.3 * static_cast<double>(i));
+  }
+  dump("bd.x", data.features);
+  dump("bd.rhs", rhs);
+  dump("bd.solve", A_ldlt.solve(rhs));
+  dump("bd.sqrt_solve", A_ldlt.sqrt_solve(rhs));
+  dump("bd.log_determinant", A_ldlt.log_determinant());
+  dump("bd.dense", K_ff.toDense());
+  // QR of a tall matrix: B = [A^-1/2 rhs-like columns ; I]
+  MatrixXd B(340, 40);
+  std::mt19937 gen(3);
+  std::normal_distribution<double> nd(0., 1.);
+  for (Index j = 0; j < 40; ++j) {
+    for (Index i = 0; i < 340; ++i) {
+      B(i, j) = nd(gen) + (i == j ? 3. : 0.);
+    }
+  }
+  const auto qr = ab::DenseQRImplementation::compute(B, nullptr);
+  EXPECT(qr->rank() == 40 && qr->rows() == 340 && qr->cols() == 40);
+  const MatrixXd R = ab::get_R(*qr);
+  EXPECT(R(5, 2) == 0. && R(2, 2) > 0.);
+  dump("qr.B", B);
+  dump("qr.R", R);
+  MatrixXd r2(40, 2);
+  for (Index i = 0; i < 40; ++i) {
+    r2(i, 0) = 1. + static_cast<double>(i);
+    r2(i, 1) = std::sin(static_cast<double>(i));
+  }
+  dump("qr.rhs", r2);
+  dump("qr.sqrt_solve", ab::sqrt_solve(R, ab::get_P(*qr), r2));
+}
+
 static void scenario_not_positive_definite() {
   // Duplicate points without a noise term: K is singular.  The reference's pivoted LDLT proceeds and its
   // outputs are NaN / inf (GenericTuner maps a NaN objective to +inf, tune.hpp:164-166); the device reports
@@ -471,6 +521,7 @@ int main(int argc, char **argv) {
       scenario_sparse();
       scenario_sparse_measurement_only();
       scenario_not_positive_definite();
+      scenario_block_diagonal_and_qr();
       const ab_phase_times t = ab::Device::default_device()->timings();
       dump("kernel_launches", static_cast<double>(t.kernel_launches));
     } catch (const ab::device_error &e) {

@@ -266,3 +266,26 @@ def test_route_1b_real_reference_with_device_ldlt():
     print(res.stdout)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "0 failure(s)" in res.stdout
+
+
+def test_block_diagonal_ldlt_and_qr_concept(dumped):
+    """BlockDiagonalLDLT (linalg/block_diagonal.hpp:96-218) and the QR concept (sparse_gp.hpp:72-89,
+    linalg/qr_utils.hpp:18-53) of the layer: block solves against dense algebra on the same blocks, R^T R = B^T B
+    and sqrt_solve = R^-T P^T rhs."""
+    d = dumped
+    K = d["bd.dense"].reshape(300, 300).T
+    rhs = d["bd.rhs"].reshape(2, 300).T
+    assert_close(d["bd.solve"].reshape(2, 300).T, np.linalg.solve(K, rhs), RTOL, "block solve")
+    s = d["bd.sqrt_solve"].reshape(2, 300).T
+    assert_close(s.T @ s, rhs.T @ np.linalg.solve(K, rhs), RTOL, "sqrt_solve Gram")
+    sign, logdet = np.linalg.slogdet(K)
+    assert sign > 0 and abs(d["bd.log_determinant"][0] - logdet) <= RTOL * abs(logdet)
+    B = d["qr.B"].reshape(40, 340).T
+    R = d["qr.R"].reshape(40, 40).T
+    assert np.array_equal(R, np.triu(R)) and np.all(np.diag(R) > 0)
+    assert_close(R.T @ R, B.T @ B, 1e-12, "R^T R = B^T B")
+    _, Rnp = np.linalg.qr(B)
+    Rnp = Rnp * np.sign(np.diag(Rnp))[:, None]       # Householder R up to row signs
+    assert_close(R, Rnp, 1e-11, "R vs LAPACK")
+    r2 = d["qr.rhs"].reshape(2, 40).T
+    assert_close(d["qr.sqrt_solve"].reshape(2, 40).T, np.linalg.solve(R.T, r2), 1e-12, "R^-T rhs")
