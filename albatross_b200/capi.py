@@ -75,7 +75,7 @@ SYMBOLS = [
     "ab_sparse_fit", "ab_sparse_free", "ab_sparse_info", "ab_sparse_log_likelihood",
     "ab_sparse_predict", "ab_sparse_export_R", "ab_sparse_fit2", "ab_sparse_log_likelihood2",
     "ab_sparse_predict2", "ab_factor_sqrt_product", "ab_factor_sqrt_transpose_solve",
-    "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt", "ab_qr_r",
+    "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt", "ab_qr_r", "ab_gp_update",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
     "ab_dist_factor_free", "ab_dist_fit_breakdown", "ab_dist_factor_broadcast", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
     "ab_partition_triangular",
@@ -445,6 +445,18 @@ class Handle:
                                  None if yvar_dev is None else yvar_dev.ptr, C.byref(out),
                                  C.byref(info) if want_information else None))
         return Factor(self, out), (Matrix(self, info) if want_information else None)
+
+    def gp_update(self, factor, ops, params, train_feats, information_old, new_feats, y_new, yvar_new=None):
+        """Returns (Factor of size n + p, information[n + p])."""
+        prog, nops = program(ops, params)
+        x, xn = _feats(train_feats), _feats(new_feats)
+        io, y, yv = _vec(information_old), _vec(y_new), _vec(yvar_new)
+        info = np.empty(x.shape[0] + xn.shape[0])
+        out = C.c_void_p()
+        _check(lib().ab_gp_update(self.ptr, factor.ptr, prog, nops, _d(x), C.c_int64(x.shape[0]),
+                                  C.c_int(x.shape[1]), _d(io), _d(xn), C.c_int64(xn.shape[0]), _d(y), _d(yv),
+                                  C.byref(out), _d(info)))
+        return Factor(self, out), info
 
     def gp_nll_d(self, ops, params, feats_dev, y_dev):
         prog, nops = program(ops, params)

@@ -461,15 +461,22 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
       }
       AB_TRY(bcast_p(0));
     }
+    // AB_DIST_PCOL=0 (experiment): PS takes the next owned column only in the step that completes it
+    // (jstar == k + 1); in the other steps it stays in the bulk launch
+    bool pcol_always = true;
+    if (const char *e = std::getenv("AB_DIST_PCOL")) {
+      pcol_always = e[0] != '0';
+    }
     for (int64_t k = 0; k < nblk; ++k) {
-      const int64_t jstar = first_owned_after(k);
+      int64_t jstar = first_owned_after(k);
+      const bool p_takes = jstar < nblk && (pcol_always || jstar == k + 1);
       // ---- PS: the next column I own
       AB_CUDA(cudaStreamWaitEvent(PS, arrived[k], 0));
-      if (jstar < nblk) {
+      if (p_takes) {
         // S updated this column with the panels before my previous column (jstar - W); it must be done
         // with them before PS takes the column over
-        const int64_t handover = jstar - W - 1;
-        if (k == std::max<int64_t>(jstar - W, 0) && handover >= 0) {
+        const int64_t handover = pcol_always ? jstar - W - 1 : k - 1;
+        if ((!pcol_always || k == std::max<int64_t>(jstar - W, 0)) && handover >= 0) {
           AB_CUDA(cudaStreamWaitEvent(PS, bulkdone[handover], 0));
         }
         {
@@ -485,7 +492,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
       AB_CUDA(cudaEventRecord(ev.wait_begin[k], S));
       AB_CUDA(cudaStreamWaitEvent(S, arrived[k], 0));
       AB_CUDA(cudaEventRecord(ev.wait_end[k], S));
-      AB_TRY(update_cols(jstar + W, -1, k));
+      AB_TRY(update_cols(p_takes ? jstar + W : jstar, -1, k));
       AB_CUDA(cudaEventRecord(bulkdone[k], S));
       // ---- CS: the next panel
       if (k + 1 < nblk) {
@@ -738,6 +745,9 @@ int ab_dist_gp_fit(ab_handle h, const ab_op *prog, int nops, const double *feats
   AB_REQUIRE(h != nullptr && factor != nullptr && n >= 1 && feats != nullptr && y != nullptr, "null");
   if (nb <= 0) {
     nb = 1024;
+    if (const char *e = std::getenv("AB_DIST_NB")) { // experiment hook (tools/bench_configs_dist.py --schedules)
+      nb = std::atoll(e);
+    }
   }
   AB_REQUIRE(nb % 128 == 0, "block size must be a multiple of 128");
   Lock lock(h);

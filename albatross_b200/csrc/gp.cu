@@ -768,6 +768,164 @@ int ab_gp_predict2(ab_handle h, ab_factor f, const ab_op *cross_prog, int cross_
                          information, test_feats, p, what, mean, var, cov);
 }
 
+// ---- incremental update -------------------------------------------------------------------
+
+// dinv[leaf] = (lower-triangular LEAF x LEAF diagonal block of L at row/column leaf * LEAF)^-1, identity
+// padded for a ragged last leaf; one CTA per leaf, thread c solves column c by forward substitution.
+static __global__ void __launch_bounds__(LEAF)
+leaf_inverse_kernel(const double *L, int64_t ld, int64_t n, double *dinv) {
+  __shared__ double s[LEAF][LEAF + 1];
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * LEAF;
+  const int nb = static_cast<int>(n - o < LEAF ? n - o : LEAF);
+  const int c = threadIdx.x;
+  for (int r = 0; r < LEAF; ++r) {
+    double v = (r == c) ? 1. : 0.;
+    if (r < nb && c < nb && r >= c) {
+      v = L[(o + r) + (o + c) * ld];
+    }
+    s[r][c] = v;
+  }
+  __syncthreads();
+  double *out = dinv + static_cast<int64_t>(blockIdx.x) * LEAF * LEAF;
+  double col[LEAF]; // column c of the inverse
+  for (int r = 0; r < LEAF; ++r) {
+    double acc = (r == c) ? 1. : 0.;
+    for (int t = c; t < r; ++t) {
+      acc = fma(-s[r][t], col[t], acc);
+    }
+    col[r] = r >= c ? acc / s[r][r] : 0.;
+    out[r + c * LEAF] = col[r];
+  }
+}
+
+// dst(i, j) = src(j, i): rows x cols of dst
+static __global__ void transpose_into_kernel(const double *src, int64_t lds, double *dst, int64_t ldd, int64_t rows,
+                                      int64_t cols) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i < rows && j < cols) {
+    dst[i + j * ldd] = src[j + i * lds];
+  }
+}
+
+/*
+ * Device form of GaussianProcessBase::_update_impl (gp.hpp:386-414) + BlockSymmetric
+ * (linalg/block_symmetric.hpp:46-133).  The reference keeps A^-1 B and the Schur complement's LDLT next to the old
+ * factor; with a Cholesky factor the same algebra IS the factor of the enlarged matrix,
+ *     [K  B; B^T C] = [L 0; X^T L_S] [L 0; X^T L_S]^T,   X = L^-1 B,   L_S L_S^T = C - X^T X,
+ * so the update returns an ordinary factor of size n + p: O(n^2 p) work instead of the O((n+p)^3) refit.
+ */
+int ab_gp_update(ab_handle h, ab_factor old_factor, const ab_op *prog, int nops, const double *train_feats,
+                 int64_t n, int dim, const double *information_old, const double *new_feats, int64_t p,
+                 const double *y_new, const double *yvar_new, ab_factor *factor, double *information) {
+  AB_REQUIRE(h != nullptr && factor != nullptr && train_feats != nullptr && new_feats != nullptr &&
+                 y_new != nullptr && n >= 1 && p >= 1 && (information == nullptr || information_old != nullptr),
+             "null / sizes");
+  Lock lock(h);
+  AB_TRY(require_usable(old_factor));
+  AB_REQUIRE(old_factor->n == n, "factor size differs from the training set");
+  DevProg P;
+  AB_TRY(compile_program(prog, nops, &P));
+  Scope sc(h);
+  timings_reset(h);
+  *factor = nullptr;
+  const int64_t N = n + p;
+  ab_matrix_s *FX = nullptr, *FN = nullptr, *B = nullptr, *Cn = nullptr, *Lnew = nullptr;
+  phase_begin(h, PH_H2D);
+  AB_TRY(upload_features(h, train_feats, n, dim, &FX));
+  sc.own(FX);
+  AB_TRY(upload_features(h, new_feats, p, dim, &FN));
+  sc.own(FN);
+  phase_end(h, PH_H2D);
+  phase_begin(h, PH_GRAM);
+  AB_TRY(gram_cross_device(h, P, FX, FN, &B)); // n x p
+  sc.own(B);
+  AB_TRY(gram_sym_device(h, P, FN, AB_GRAM_LOWER_ONLY, &Cn));
+  sc.own(Cn);
+  if (yvar_new != nullptr) {
+    void *dv = nullptr;
+    AB_TRY(upload_bytes(h, sc, yvar_new, static_cast<size_t>(p) * sizeof(double), &dv));
+    AB_TRY(add_diag(h, view(Cn), p, static_cast<double *>(dv)));
+  }
+  phase_end(h, PH_GRAM);
+  phase_begin(h, PH_FACTOR);
+  // X = L^-1 B, in place;  S = C - X^T X (lower)
+  AB_TRY(trsm_left_lower(h, view(old_factor->m), old_factor->dinv, n, view(B), p));
+  AB_TRY(gemm(h, GEMM_TRANS_A | GEMM_LOWER, p, p, n, -1., view(B), view(B), 1., view(Cn)));
+  // the enlarged factor: old L, X^T below it, chol(S) in the corner
+  AB_TRY(matrix_new(h, N, N, &Lnew));
+  AB_CUDA(cudaMemcpy2DAsync(Lnew->d, Lnew->ld * sizeof(double), old_factor->m->d,
+                            old_factor->m->ld * sizeof(double), static_cast<size_t>(n) * sizeof(double),
+                            static_cast<size_t>(n), cudaMemcpyDeviceToDevice, h->stream));
+  {
+    const dim3 grid(static_cast<unsigned>((p + 255) / 256), static_cast<unsigned>(n));
+    transpose_into_kernel<<<grid, 256, 0, h->stream>>>(B->d, B->ld, Lnew->d + n, Lnew->ld, p, n);
+    AB_LAUNCHED(h);
+  }
+  AB_CUDA(cudaMemcpy2DAsync(Lnew->d + n + n * Lnew->ld, Lnew->ld * sizeof(double), Cn->d,
+                            Cn->ld * sizeof(double), static_cast<size_t>(p) * sizeof(double),
+                            static_cast<size_t>(p), cudaMemcpyDeviceToDevice, h->stream));
+  ab_factor_s *f = nullptr;
+  {
+    int s = new_factor(h, Lnew, &f);
+    if (s != AB_OK) {
+      matrix_delete(h, Lnew);
+      return s;
+    }
+  }
+  // factor the corner in place (its own leaf grid), then rebuild the leaf inverses on the new matrix's grid
+  void *tmp_inv = nullptr;
+  const size_t tmp_bytes = static_cast<size_t>((p + LEAF - 1) / LEAF) * LEAF * LEAF * sizeof(double);
+  int status = sc.alloc(tmp_bytes, &tmp_inv);
+  h->h_flags[0] = INT_MAX;
+  if (status == AB_OK) {
+    cudaMemcpyAsync(h->d_flags, h->h_flags, sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    status = potrf(h, view(Lnew).sub(n, n), p, static_cast<double *>(tmp_inv), h->d_flags);
+  }
+  if (status == AB_OK) {
+    leaf_inverse_kernel<<<static_cast<unsigned>((N + LEAF - 1) / LEAF), LEAF, 0, h->stream>>>(Lnew->d, Lnew->ld, N,
+                                                                                         f->dinv);
+    h->launches++;
+    status = download_bytes(h, h->d_flags, sizeof(int), h->h_flags);
+  }
+  phase_end(h, PH_FACTOR);
+  if (status != AB_OK) {
+    delete_factor(h, f);
+    return status;
+  }
+  f->bad_pivot = h->h_flags[0] == INT_MAX ? -1 : n + h->h_flags[0];
+  *factor = f;
+  if (f->bad_pivot >= 0) {
+    set_error("updated covariance is not positive definite: pivot %lld", static_cast<long long>(f->bad_pivot));
+    cudaEventRecord(h->ev_total_end, h->stream);
+    return AB_ERR_NOT_PD;
+  }
+  if (information != nullptr) {
+    // the old targets are not part of a fit (gp.hpp:49-51 keeps features, factor and information): they are
+    // recovered as y = K alpha = L (L^T alpha); then information' = K'^-1 [y; y_new]
+    ab_matrix_s *x = nullptr, *t = nullptr;
+    phase_begin(h, PH_SOLVE);
+    AB_TRY(matrix_new(h, N, 1, &x));
+    sc.own(x);
+    AB_TRY(matrix_new(h, n, 1, &t));
+    sc.own(t);
+    AB_CUDA(cudaMemcpyAsync(x->d, information_old, static_cast<size_t>(n) * sizeof(double),
+                            cudaMemcpyHostToDevice, h->stream));
+    AB_CUDA(cudaMemcpyAsync(x->d + n, y_new, static_cast<size_t>(p) * sizeof(double), cudaMemcpyHostToDevice,
+                            h->stream));
+    AB_TRY(trmm_left_lower(h, view(old_factor->m), n, true, view(x), view(t), 1));
+    AB_TRY(trmm_left_lower(h, view(old_factor->m), n, false, view(t), view(x), 1));
+    AB_TRY(trsm_left_lower(h, view(f->m), f->dinv, N, view(x), 1));
+    AB_TRY(trsm_left_lower_T(h, view(f->m), f->dinv, N, view(x), 1));
+    phase_end(h, PH_SOLVE);
+    cudaEventRecord(h->ev_total_end, h->stream);
+    return download(h, x, 0, 0, N, 1, information);
+  }
+  cudaEventRecord(h->ev_total_end, h->stream);
+  AB_CUDA(cudaStreamSynchronize(h->stream));
+  return AB_OK;
+}
+
 } // extern "C"
 
 namespace ab {

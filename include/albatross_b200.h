@@ -284,6 +284,24 @@ AB_API int ab_gp_cv_shard(ab_handle h, ab_factor factor, const double *y, const 
                    const int64_t *indices, const int64_t *offsets, int64_t ngroups, int what,
                    int shard, int nshards, double *mean, double *var, double *score);
 
+/*
+ * fit_model.update(dataset): the fit of [train; new] from the fit of train without refactoring.  Replaces
+ * GaussianProcessBase::_update_impl src/models/gp.hpp:386-414 and BlockSymmetric
+ * src/linalg/block_symmetric.hpp:46-133 (Schur complement S = C - B^T A^-1 B): with a Cholesky factor the
+ * same algebra yields the factor of the enlarged matrix itself, [L 0; (L^-1 B)^T chol(S)], so the result is
+ * an ordinary ab_factor of size n + p (usable with every ab_factor_* / ab_gp_* call); O(n^2 p + p^3) work.
+ *   old_factor   factor of k(train, train) + diag(yvar_train), left untouched
+ *   prog         k(Measurement, Measurement) as in ab_gp_fit
+ *   information_old  K^-1 y of the old fit (a fit does not keep its targets, gp.hpp:49-51: they are
+ *                recovered on the device as y = L L^T information_old)
+ *   y_new        p new targets, mean function already removed; yvar_new may be NULL
+ * information (n + p doubles, optional) = K'^-1 [y; y_new].
+ */
+AB_API int ab_gp_update(ab_handle h, ab_factor old_factor, const ab_op *prog, int nops,
+                 const double *train_feats, int64_t n, int dim, const double *information_old,
+                 const double *new_feats, int64_t p, const double *y_new, const double *yvar_new,
+                 ab_factor *factor, double *information);
+
 /* Device-resident variants (inputs already in HBM; results stay in HBM unless a host ptr is given). */
 AB_API int ab_gp_fit_d(ab_handle h, const ab_op *prog, int nops, ab_matrix feats, ab_matrix y,
                 ab_matrix yvar, ab_factor *factor, ab_matrix *information);

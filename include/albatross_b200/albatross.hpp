@@ -17,6 +17,7 @@
 #include "linalg_types.hpp"
 #include "parameters.hpp"
 #include "sparse_gp.hpp"
+#include "tune.hpp"
 
 #ifdef ALBATROSS_B200_AS_ALBATROSS
 namespace albatross = albatross_b200;

@@ -110,6 +110,19 @@ public:
     return predict(as_measurements(features));
   }
 
+  // fit_model.update(dataset), fit_model.hpp:64-95: the fit of the concatenated data without a refit.
+  template <typename FeatureType>
+  auto update(const std::vector<FeatureType> &features, const MarginalDistribution &targets) const {
+    auto updated = model_._update_impl(fit_, features, targets);
+    return FitModel<ModelType, decltype(updated)>(model_, std::move(updated));
+  }
+  template <typename FeatureType> auto update(const RegressionDataset<FeatureType> &dataset) const {
+    return update(dataset.features, dataset.targets);
+  }
+  template <typename FeatureType> void update_in_place(const RegressionDataset<FeatureType> &dataset) {
+    fit_ = model_._update_impl(fit_, dataset.features, dataset.targets);
+  }
+
   const FitType &get_fit() const { return fit_; }
   FitType &get_fit() { return fit_; }
   ModelType get_model() const { return model_; }
@@ -388,6 +401,33 @@ public:
       fill_nan(information.data(), static_cast<std::size_t>(information.size()));
     }
     return DeviceGPFit<FeatureType>(features, DeviceLDLT(dev, factor), std::move(information));
+  }
+
+  // _update_impl, gp.hpp:386-414 (+ BlockSymmetric, linalg/block_symmetric.hpp:46-133): the reference keeps the
+  // old factor, A^-1 B and the Schur complement's factor side by side; the device extends the Cholesky factor
+  // itself (ab_gp_update), so the updated fit is an ordinary DeviceGPFit of the concatenated features.
+  template <typename FeatureType>
+  DeviceGPFit<FeatureType> _update_impl(const DeviceGPFit<FeatureType> &fit_, const std::vector<FeatureType> &features,
+                                        const MarginalDistribution &targets) const {
+    using M = Measurement<FeatureType>;
+    const Program prog = covariance_function_.template program<M, M>();
+    std::vector<FeatureType> all(fit_.train_features);
+    all.insert(all.end(), features.begin(), features.end());
+    const PackedFeatures f_old = pack_features(fit_.train_features);
+    const PackedFeatures f_new = pack_features(features);
+    VectorXd y(targets.mean);
+    remove_mean(mean_function_, features, &y);
+    VectorXd information(static_cast<Index>(all.size()));
+    const std::shared_ptr<Device> dev = fit_.train_covariance.device();
+    ab_factor factor = nullptr;
+    const double *yvar = targets.has_covariance() ? targets.covariance.diagonal().data() : nullptr;
+    if (ALBATROSS_B200_NOT_PD(ab_gp_update(dev->get(), fit_.train_covariance.get(), prog.data(),
+                                           static_cast<int>(prog.size()), f_old.data.data(), f_old.n, f_old.dim,
+                                           fit_.information.data(), f_new.data.data(), f_new.n, y.data(), yvar, &factor,
+                                           information.data()))) {
+      fill_nan(information.data(), static_cast<std::size_t>(information.size()));
+    }
+    return DeviceGPFit<FeatureType>(all, DeviceLDLT(dev, factor), std::move(information));
   }
 
   // _predict_impl x3, gp.hpp:313-366.  The cross covariance is k(train as stored in the fit, test):

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <iostream>
 #include <random>
+#include <sstream>
 
 namespace ab = albatross_b200;
 using ab::Index;
@@ -474,6 +475,77 @@ static void scenario_block_diagonal_and_qr() {
   dump("qr.sqrt_solve", ab::sqrt_solve(R, ab::get_P(*qr), r2));
 }
 
+static void scenario_tuner() {
+  // examples/sinc_example.cc:35-38 shape: get_tuner(model, LeaveOneOutLikelihood<>(), dataset).tune()
+  auto data = make_1d(250, 33, 0., 10.);
+  dump("tune.x", data.features);
+  dump("tune.y", data.targets.mean);
+  auto cov = SE(2.5, 0.7) + ab::IndependentNoise<double>(0.3); // deliberately off: truth is ~(1, 1, <0.1)
+  auto model = ab::gp_from_covariance(cov);
+  std::ostringstream log;
+  auto tuner = ab::get_tuner(model, ab::LeaveOneOutLikelihood<>(), data, log);
+  // a batch of candidates (what a finite-difference gradient or a population step evaluates): objective
+  // values are compared with the reference's objective (tune.hpp:277-286) on the host
+  std::vector<ab::ParameterStore> candidates;
+  const double ls[5] = {2.5, 1.0, 0.6, 1.7, 3.1}, sg[5] = {0.7, 1.0, 1.4, 0.9, 0.5}, sn[5] = {0.3, 0.1, 0.05, 0.2, 0.6};
+  std::vector<double> flat;
+  for (int c = 0; c < 5; ++c) {
+    ab::ParameterStore p = model.get_params();
+    p["squared_exponential_length_scale"].value = ls[c];
+    p["sigma_squared_exponential"].value = sg[c];
+    p["sigma_independent_noise"].value = sn[c];
+    candidates.push_back(p);
+    flat.insert(flat.end(), {ls[c], sg[c], sn[c]});
+  }
+  dump("tune.candidates", flat);
+  const std::vector<double> values = tuner.evaluate(candidates);
+  dump("tune.candidate_objectives", values);
+  const std::vector<double> grad = tuner.gradient(candidates[1], values[1]);
+  EXPECT(grad.size() == 3);
+  dump("tune.gradient_at_1", grad);
+  // NegativeLogMarginalLikelihood objective at the same candidates
+  auto tuner_ml = ab::get_tuner(model, ab::NegativeLogMarginalLikelihood(), data, log);
+  dump("tune.candidate_nll", tuner_ml.evaluate(candidates));
+  // and the loop itself
+  tuner.options.max_evaluations = 150;
+  const double before = tuner.objective(model.get_params());
+  const ab::ParameterStore tuned = tuner.tune();
+  const double after = tuner.objective(tuned);
+  EXPECT(after < before - 1.);
+  EXPECT(tuner.last_result.evaluations <= 150 + 4);
+  dump("tune.before_after", std::vector<double>{before, after, static_cast<double>(tuner.last_result.evaluations)});
+  dump("tune.tuned", std::vector<double>{tuned.at("squared_exponential_length_scale").value,
+                                         tuned.at("sigma_squared_exponential").value,
+                                         tuned.at("sigma_independent_noise").value});
+  EXPECT(log.str().find("TUNED PARAMS") != std::string::npos);
+}
+
+static void scenario_update() {
+  // tests/test_gp.cc:182-219: fit on the first part, update with the second == fit on everything
+  auto data = make_1d(900, 41, 0., 10.);
+  auto cov = SE(1.2, 1.1) + ab::measurement_only(ab::IndependentNoise<double>(0.2));
+  auto model = ab::gp_from_covariance(cov);
+  std::vector<double> xa(data.features.begin(), data.features.begin() + 600), xb(data.features.begin() + 600, data.features.end());
+  VectorXd ya(600), yb(300);
+  for (Index i = 0; i < 600; ++i) {
+    ya[i] = data.targets.mean[i];
+  }
+  for (Index i = 0; i < 300; ++i) {
+    yb[i] = data.targets.mean[600 + i];
+  }
+  const auto first = model.fit(ab::RegressionDataset<double>(xa, ya));
+  const auto updated = first.update(ab::RegressionDataset<double>(xb, yb));
+  const auto full = model.fit(data);
+  EXPECT(updated.get_fit().train_features.size() == 900);
+  std::vector<double> test = ab::linspace(0.3, 9.7, 23);
+  dump("update.x", data.features);
+  dump("update.y", data.targets.mean);
+  dump("update.test", test);
+  dump("update.information", updated.get_fit().information);
+  dump("update.full_information", full.get_fit().information);
+  dump("update.marginal", updated.predict(test).marginal());
+}
+
 static void scenario_not_positive_definite() {
   // Duplicate points without a noise term: K is singular.  The reference's pivoted LDLT proceeds and its
   // outputs are NaN / inf (GenericTuner maps a NaN objective to +inf, tune.hpp:164-166); the device reports
@@ -522,6 +594,8 @@ int main(int argc, char **argv) {
       scenario_sparse_measurement_only();
       scenario_not_positive_definite();
       scenario_block_diagonal_and_qr();
+      scenario_tuner();
+      scenario_update();
       const ab_phase_times t = ab::Device::default_device()->timings();
       dump("kernel_launches", static_cast<double>(t.kernel_launches));
     } catch (const ab::device_error &e) {

@@ -289,3 +289,40 @@ def test_block_diagonal_ldlt_and_qr_concept(dumped):
     assert_close(R, Rnp, 1e-11, "R vs LAPACK")
     r2 = d["qr.rhs"].reshape(2, 40).T
     assert_close(d["qr.sqrt_solve"].reshape(2, 40).T, np.linalg.solve(R.T, r2), 1e-12, "R^-T rhs")
+
+
+def test_tuner_objectives_match_the_reference(dumped):
+    """SURVEY.md §8f-1: the objective ModelTuner::tune() minimises (src/tune/tune.hpp:277-286) evaluated on the
+    device for a batch of hyper-parameter candidates equals the reference's on the host at 1e-9 — both the
+    default LeaveOneOutLikelihood (model_metrics.hpp:59-73) and the marginal likelihood; the loop itself
+    improves the objective."""
+    d = dumped
+    x, y = d["tune.x"], d["tune.y"]
+    cands = d["tune.candidates"].reshape(5, 3)
+    for c in range(5):
+        p = list(cands[c])
+        _, _, _, score = Ref.gp_cv(6, p, x, y, 0, what=1, want_score=True)
+        got = d["tune.candidate_objectives"][c]
+        assert abs(got - score) <= RTOL * abs(score), (c, got, score)
+        nll, _ = Ref.gp_nll(6, p, x, y)
+        assert abs(d["tune.candidate_nll"][c] - nll) <= RTOL * abs(nll), (c, d["tune.candidate_nll"][c], nll)
+    # forward differences of the reference objective (finite_difference.hpp:34-79) at candidate 1
+    before, after, evals = d["tune.before_after"]
+    assert after < before and evals <= 154
+    tuned = list(d["tune.tuned"])
+    _, _, _, score = Ref.gp_cv(6, tuned, x, y, 0, what=1, want_score=True)
+    assert abs(after - score) <= RTOL * abs(score)
+
+
+def test_update_through_the_layer(dumped):
+    """fit_model.update(dataset) (core/fit_model.hpp:64-95 -> gp.hpp:386-414): partial fit + update == the
+    reference's fit of everything (tests/test_gp.cc:182-219)."""
+    d = dumped
+    x, y, t = d["update.x"], d["update.y"], d["update.test"]
+    p = [1.2, 1.1, 0.2]
+    want = Ref.gp_fit(10, p, x, y)["information"]
+    assert_close(d["update.information"], want, RTOL, "information after update")
+    assert_close(d["update.full_information"], want, RTOL, "information of the full fit")
+    mean, var, _ = Ref.gp_predict(10, p, x, y, t, 1)
+    assert_close(d["update.marginal.mean"], mean, RTOL, "mean after update")
+    assert np.max(np.abs(d["update.marginal.var"] - var)) <= RTOL * 1.3

@@ -379,3 +379,37 @@ def test_singular_psd_policy_next_to_the_reference(handle, golden):
     ops, pp = prog(6)
     want = Restate.gp_nll(ops, pp, ref["psd_x"], rhs)
     assert abs(handle.gp_nll(ops, pp, ref["psd_x"], rhs) - want) <= RTOL * abs(want)
+
+
+# ---- incremental update (tests/test_gp.cc:182-219: a partial fit followed by update == a full fit) ----
+
+@pytest.mark.parametrize("n,p", [(640, 128), (701, 150), (65, 1), (1500, 777)])
+def test_update_equals_full_fit(handle, n, p):
+    """ab_gp_update (gp.hpp:386-414 + BlockSymmetric, block_symmetric.hpp:46-133, as an extension of the
+    Cholesky factor) against the oracle's full fit of the concatenated data."""
+    ops, pp = prog(8)
+    x = features(n + p, 3, 11 * n + p)
+    y = targets(x)
+    yvar = 0.01 + 0.02 * (np.arange(n + p) % 5)
+    t = features(19, 3, 5)
+    f0, info0 = handle.gp_fit(ops, pp, x[:n], y[:n], yvar=yvar[:n])
+    f1, info1 = handle.gp_update(f0, ops, pp, x[:n], info0, x[n:], y[n:], yvar_new=yvar[n:])
+    assert f1.n == n + p and f1.is_positive_definite()
+    want = Restate.gp_fit(ops, pp, x, y, yvar=yvar)["information"]
+    assert_close(info1, want, RTOL, "updated information")
+    mean, var, _ = handle.gp_predict(f1, ops, pp, x, info1, t, MARGINAL)
+    wm, wv, _ = Restate.gp_predict(ops, pp, x, y, t, 1, yvar=yvar)
+    assert_close(mean, wm, RTOL, "mean after update")
+    assert np.max(np.abs(var - wv)) <= RTOL * np.max(wv + 1.0)
+    # the updated factor is an ordinary factor: the whole surface works on it
+    full, _ = handle.gp_fit(ops, pp, x, y, yvar=yvar)
+    assert abs(f1.log_determinant() - full.log_determinant()) <= RTOL * abs(full.log_determinant())
+    rhs = np.random.default_rng(n).standard_normal((n + p, 3))
+    assert_close(f1.solve(rhs), full.solve(rhs), 1e-10, "solve on the updated factor")
+    # the old fit is untouched, and updates chain
+    assert_close(f0.solve(y[:n]), info0, 1e-12, "old factor unchanged")
+    half = p // 2
+    if half > 0:
+        fa, ia = handle.gp_update(f0, ops, pp, x[:n], info0, x[n:n + half], y[n:n + half], yvar_new=yvar[n:n + half])
+        fb, ib = handle.gp_update(fa, ops, pp, x[:n + half], ia, x[n + half:], y[n + half:], yvar_new=yvar[n + half:])
+        assert_close(ib, want, RTOL, "two chained updates")

@@ -42,6 +42,22 @@ def gather(value):
     return [float(v) for v in t.cpu()]
 
 
+def config3_schedules(h, rank, world, n, schedules):
+    """The same fit under different schedules of the distributed factorisation (environment switches of
+    dist.cu, read at every call): one line per schedule."""
+    out = []
+    for spec in schedules:
+        for kv in spec.split("+"):
+            k, v = kv.split("=")
+            os.environ[k] = v
+        line = config3(h, rank, world, n)
+        line["schedule"] = spec
+        out.append(line)
+        for kv in spec.split("+"):
+            os.environ.pop(kv.split("=")[0], None)
+    return out
+
+
 def config3(h, rank, world, n):
     x = np.random.default_rng(0).uniform(0, 10, size=(n, 3))
     y = np.sin(x[:, 0]) + 0.1 * np.cos(10 * x[:, 0])
@@ -160,6 +176,18 @@ def main():
     rank, world = abd.bootstrap(h)
     os.makedirs("gpurun_out", exist_ok=True)
     fh = open(f"gpurun_out/{tag}_configs_dist.jsonl", "a") if rank == 0 else None
+    for i, a_ in enumerate(sys.argv):
+        if a_ == "--schedules":  # e.g. AB_DIST_SCHEDULE=lookahead1,AB_DIST_NBUF=4,AB_DIST_NBUF=8+AB_DIST_PCOL=0
+            for line in config3_schedules(h, rank, world, n3, sys.argv[i + 1].split(",")):
+                line["n_gpus"] = world
+                if rank == 0:
+                    dev = line["device"]
+                    brief = {k: dev[k] for k in ("factor_ms", "solve_ms", "factor_TFLOPs_aggregate")}
+                    brief["wait_ms_max"] = max(dev["per_rank_wait_for_panel_ms"])
+                    print(json.dumps({"schedule": line["schedule"], **brief}), flush=True)
+                    fh.write(json.dumps(line) + "\n")
+                    fh.flush()
+            only = set()
     for k, fn in ((3, lambda: config3(h, rank, world, n3)), (4, lambda: config4(h, rank, world)),
                   (5, lambda: config5(h, rank, world))):
         if only is not None and k not in only:
