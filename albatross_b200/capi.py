@@ -75,7 +75,7 @@ SYMBOLS = [
     "ab_sparse_fit", "ab_sparse_free", "ab_sparse_info", "ab_sparse_log_likelihood",
     "ab_sparse_predict", "ab_sparse_export_R", "ab_sparse_fit2", "ab_sparse_log_likelihood2",
     "ab_sparse_predict2", "ab_factor_sqrt_product", "ab_factor_sqrt_transpose_solve",
-    "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt", "ab_qr_r", "ab_gp_update",
+    "ab_factor_sqrt_transpose", "ab_factor_diagonal_sqrt", "ab_qr_r", "ab_gp_update", "ab_factor_import_packed",
     "ab_dist_unique_id", "ab_dist_init", "ab_dist_finalize", "ab_dist_info", "ab_dist_gp_fit",
     "ab_dist_factor_free", "ab_dist_fit_breakdown", "ab_dist_factor_broadcast", "ab_dist_block_owner", "ab_dist_gram_rows", "ab_dist_gp_cv",
     "ab_partition_triangular",
@@ -583,6 +583,15 @@ class Handle:
                                     C.c_int(x.shape[1]), _d(y), _d(yv), C.c_int64(nb),
                                     C.byref(out), _d(info), C.byref(nll)))
         return DistFactor(self, out), info, nll.value
+
+    def import_packed(self, LD, transpositions=None):
+        """Factor from Eigen::SerializableLDLT's packed form (lower triangle of LD + transpositions)."""
+        LDf = np.asfortranarray(LD, dtype=np.float64)
+        n = LDf.shape[0]
+        tr = None if transpositions is None else np.ascontiguousarray(transpositions, dtype=np.int64)
+        out = C.c_void_p()
+        _check(lib().ab_factor_import_packed(self.ptr, _d(LDf), _i(tr), C.c_int64(n), C.byref(out)))
+        return Factor(self, out)
 
     def qr_r(self, B):
         """R (upper triangular, P = I) of a thin QR of the host matrix B."""

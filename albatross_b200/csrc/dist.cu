@@ -295,6 +295,13 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
       AB_TRY(add_diag(h, dst, width(j), d_yvar + r0));
     }
   }
+  // pivot floors from the ORIGINAL diagonal (linalg.cu potrf): a block's diagonal is ~0 after the trailing
+  // updates when the matrix is singular, so the floor must be taken now
+  void *d_floor = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(std::max<int64_t>(nloc, 1) * nb) * sizeof(double), &d_floor));
+  for (int64_t j = me; j < nblk; j += W) {
+    AB_TRY(pivot_floor(h, colblk(j).sub(j * nb, 0), width(j), static_cast<double *>(d_floor) + (j / W) * nb));
+  }
   phase_end(h, PH_GRAM);
 
   // ---- factorisation --------------------------------------------------------------------------
@@ -314,7 +321,10 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   if (const char *e = std::getenv("AB_DIST_SCHEDULE")) {
     pipelined = std::strcmp(e, "lookahead1") != 0;
   }
-  int64_t NBUF = pipelined ? 4 : 2;
+  // packed-panel buffers: 2 on two ranks (measured best: 1458 vs 1558 ms with 4 at N = 65 536), 4 beyond
+  // (3099 vs 3126 with 2 at N = 131 072 on 8 GPUs; 8 buffers: 3345 — a chain far ahead of the updates competes
+  // with them for HBM); profiles/r02i_*, r02j_*, r02k_*
+  int64_t NBUF = pipelined ? (W <= 2 ? 2 : 4) : 2;
   if (const char *e = std::getenv("AB_DIST_NBUF")) {
     NBUF = std::max<int64_t>(2, std::min<int64_t>(16, std::atoll(e)));
   }
@@ -345,7 +355,8 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     const MatView D = colblk(k).sub(r0, 0);
     AB_CUDA(cudaEventRecord(ev.panel_begin[k], PS));
     ev.owned[static_cast<size_t>(k)] = 1;
-    AB_TRY(potrf(h, D, wk, dinv_of(k), static_cast<int *>(d_bad) + k));
+    AB_TRY(potrf(h, D, wk, dinv_of(k), static_cast<int *>(d_bad) + k,
+                 static_cast<double *>(d_floor) + (k / W) * nb));
     AB_TRY(trsm_right_lower_T(h, D, dinv_of(k), wk, D.sub(wk, 0), hk - wk));
     const MatView Pk = panel(k);
     AB_CUDA(cudaMemcpy2DAsync(Pk.p, Pk.ld * sizeof(double), D.p, D.ld * sizeof(double),
@@ -744,7 +755,11 @@ int ab_dist_gp_fit(ab_handle h, const ab_op *prog, int nops, const double *feats
                    double *information, double *nll) {
   AB_REQUIRE(h != nullptr && factor != nullptr && n >= 1 && feats != nullptr && y != nullptr, "null");
   if (nb <= 0) {
-    nb = 1024;
+    // The panel chain (apply panel -> potrf -> TRSM -> pack -> broadcast) is sequential across the ranks and
+    // its cost per step grows with nb^2 while a rank's share of the trailing update shrinks with 1/world:
+    // narrower block columns from 4 ranks on (N = 131 072 on 8 GPUs: nb 1024 / 768 / 640 / 512 = 3165 / 3138 /
+    // 3127 / 3126 ms, waiting for a panel 143 -> 66 ms; profiles/r02m_*), 1024 below (deeper DMMA k-loop)
+    nb = h->world >= 4 ? 512 : 1024;
     if (const char *e = std::getenv("AB_DIST_NB")) { // experiment hook (tools/bench_configs_dist.py --schedules)
       nb = std::atoll(e);
     }

@@ -33,6 +33,7 @@ namespace {
 
 constexpr int TBM = 128, TBN = 64, TBK = 16;
 constexpr int TSTAGES = 4;
+constexpr int TGROUP = 8; // tile columns per rasterisation group
 constexpr int TWARPS_M = 4, TWARPS_N = 2;
 constexpr int TTHREADS = 32 * TWARPS_M * TWARPS_N;
 constexpr int BOX_ROWS = 16;                                 // 16 doubles = 128 bytes: the swizzle span
@@ -90,12 +91,21 @@ __device__ __forceinline__ unsigned swz(int r, int kk) {
 __global__ void __launch_bounds__(TTHREADS, 2)
 gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    int64_t m, int64_t n, int64_t k, double alpha, double beta, double *C, int64_t ldc,
-                   int tiles_m, int lower, int vec_ok, int cyc_blk, int64_t cyc_stride, int64_t b_row0) {
+                   int tiles_m, int tiles_n, int lower, int vec_ok, int cyc_blk, int64_t cyc_stride,
+                   int64_t b_row0) {
   extern __shared__ __align__(1024) unsigned char tsmem[];
   __shared__ __align__(8) unsigned long long bars[2 * TSTAGES]; // full[0..S), empty[S..2S)
 
-  const int64_t m0 = static_cast<int64_t>(blockIdx.x % tiles_m) * TBM;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x / tiles_m) * TBN;
+  // Tile order: groups of TGROUP tile columns, the tiles of one tile row of a group next to each other, so
+  // that the ~296 CTAs resident at any time cover 37 tile rows x 8 tile columns (41 MB of operands) instead
+  // of 296 tile rows x 1 tile column (297 MB): the A panel of a trailing update (up to 1 GB) is then streamed
+  // from HBM once per GROUP of tile columns instead of once per tile column.
+  const int gidx = static_cast<int>(blockIdx.x) / (TGROUP * tiles_m);
+  const int gfirst = gidx * TGROUP;
+  const int gsize = tiles_n - gfirst < TGROUP ? tiles_n - gfirst : TGROUP;
+  const int gin = static_cast<int>(blockIdx.x) - gidx * TGROUP * tiles_m;
+  const int64_t m0 = static_cast<int64_t>(gin / gsize) * TBM;
+  const int64_t n0 = static_cast<int64_t>(gfirst + gin % gsize) * TBN;
   // Block-cyclic B (CyclicB, linalg.cuh): column block q = n0 / cyc_blk of C multiplies the rows
   // b_row0 + q * cyc_stride + (n0 % cyc_blk) ... of B, and "lower" is measured against that stretched
   // diagonal.  cyc_blk == 0: the plain product (row n0 of B, the ordinary diagonal).
@@ -331,7 +341,7 @@ int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, dou
   AB_REQUIRE(tm * tn < (int64_t(1) << 31), "GEMM grid too large");
   const int vec_ok = aligned16(C) ? 1 : 0;
   gemm_nt_tma_kernel<<<static_cast<unsigned>(tm * tn), TTHREADS, smem, h->stream>>>(
-      mapA, mapB, m, n, k, alpha, beta, C.p, C.ld, static_cast<int>(tm), lower ? 1 : 0, vec_ok,
+      mapA, mapB, m, n, k, alpha, beta, C.p, C.ld, static_cast<int>(tm), static_cast<int>(tn), lower ? 1 : 0, vec_ok,
       cyclic ? static_cast<int>(cyc->blk) : 0, cyclic ? cyc->stride : 0, cyclic ? cyc->row0 : 0);
   AB_LAUNCHED(h);
   return AB_OK;

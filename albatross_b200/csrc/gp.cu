@@ -463,6 +463,129 @@ int ab_factor_export_packed(ab_handle h, ab_factor f, double *LD, int64_t *trans
   return AB_OK;
 }
 
+static __global__ void leaf_inverse_kernel(const double *L, int64_t ld, int64_t n, double *dinv);
+
+// M(i, j) = unit-L(i, j) * sqrt(D_j) (lower triangle, zeros above) from Eigen's packed LDLT; flags a
+// non-positive D_j.
+static __global__ void packed_to_chol_kernel(const double *LD, int64_t n, double *M, int64_t ld, int *d_bad) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (i >= n) {
+    return;
+  }
+  const double d = LD[j + j * n];
+  if (i == j && !(d > 0.)) {
+    atomicMin(d_bad, static_cast<int>(j));
+  }
+  const double s = sqrt(d);
+  M[i + j * ld] = i > j ? LD[i + j * n] * s : (i == j ? s : 0.);
+}
+
+// K(a, b) = S(max(i, j), min(i, j)) with i = inv[a], j = inv[b], for a >= b: K = P^T S P from the lower
+// triangle of S, where (P x)_i = x_{perm(i)} and inv = perm^-1.
+static __global__ void unpermute_kernel(const double *S, int64_t lds, const int64_t *inv, int64_t n, double *K,
+                                        int64_t ldk) {
+  const int64_t a = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t b = blockIdx.y;
+  if (a >= n || a < b) {
+    return;
+  }
+  const int64_t i = inv[a], j = inv[b];
+  K[a + b * ldk] = i >= j ? S[i + j * lds] : S[j + i * lds];
+}
+
+/*
+ * The reverse of ab_factor_export_packed: a device factor from Eigen::SerializableLDLT's packed form (what
+ * cereal writes, src/cereal/serializable_ldlt.hpp:18-32: lower triangle = unit L below the diagonal and D
+ * on it, plus the transpositions) so that fits serialised by the reference can be loaded onto the GPU.
+ * Identity transpositions (every file written from a device fit): L_chol = L D^1/2 directly, O(n^2).
+ * Otherwise K = P^T L D L^T P is rebuilt on the device (one DSYRK) and factored without pivoting.
+ */
+int ab_factor_import_packed(ab_handle h, const double *LD, const int64_t *transpositions, int64_t n,
+                            ab_factor *out) {
+  AB_REQUIRE(h != nullptr && LD != nullptr && out != nullptr && n >= 1, "null / size");
+  AB_REQUIRE(n <= 65535, "ab_factor_import_packed takes a dense host matrix: n <= 65535");
+  Lock lock(h);
+  Scope sc(h);
+  timings_reset(h);
+  *out = nullptr;
+  // the permutation the transpositions compose to, and whether it is the identity
+  std::vector<int64_t> perm(static_cast<size_t>(n));
+  std::iota(perm.begin(), perm.end(), int64_t(0));
+  bool identity = true;
+  if (transpositions != nullptr) {
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t j = transpositions[i];
+      AB_REQUIRE(j >= 0 && j < n, "transposition out of range");
+      if (j != i) {
+        std::swap(perm[static_cast<size_t>(i)], perm[static_cast<size_t>(j)]);
+        identity = false;
+      }
+    }
+  }
+  ab_matrix_s *M = nullptr;
+  void *d_ld = nullptr;
+  phase_begin(h, PH_H2D);
+  AB_TRY(upload_bytes(h, sc, LD, static_cast<size_t>(n) * n * sizeof(double), &d_ld));
+  phase_end(h, PH_H2D);
+  AB_TRY(matrix_new(h, n, n, &M));
+  h->h_flags[0] = INT_MAX;
+  AB_CUDA(cudaMemcpyAsync(h->d_flags, h->h_flags, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  phase_begin(h, PH_FACTOR);
+  {
+    const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(n));
+    packed_to_chol_kernel<<<grid, 256, 0, h->stream>>>(static_cast<double *>(d_ld), n, M->d, M->ld, h->d_flags);
+    AB_LAUNCHED(h);
+  }
+  int status = download_bytes(h, h->d_flags, sizeof(int), h->h_flags);
+  if (status == AB_OK && h->h_flags[0] != INT_MAX) {
+    set_error("imported LDLT has a non-positive pivot D[%d]: not positive definite", h->h_flags[0]);
+    status = AB_ERR_NOT_PD;
+  }
+  if (status != AB_OK) {
+    matrix_delete(h, M);
+    return status;
+  }
+  ab_factor_s *f = nullptr;
+  if (identity) {
+    status = new_factor(h, M, &f);
+    if (status != AB_OK) {
+      matrix_delete(h, M);
+      return status;
+    }
+    leaf_inverse_kernel<<<static_cast<unsigned>((n + LEAF - 1) / LEAF), LEAF, 0, h->stream>>>(M->d, M->ld, n, f->dinv);
+    h->launches++;
+    f->bad_pivot = -1;
+  } else {
+    sc.own(M);
+    ab_matrix_s *S = nullptr, *K = nullptr;
+    AB_TRY(matrix_new(h, n, n, &S));
+    sc.own(S);
+    AB_TRY(gemm(h, GEMM_TRANS_B | GEMM_LOWER, n, n, n, 1., view(M), view(M), 0., view(S)));
+    std::vector<int64_t> inv(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) {
+      inv[static_cast<size_t>(perm[static_cast<size_t>(i)])] = i;
+    }
+    void *d_inv = nullptr;
+    AB_TRY(upload_bytes(h, sc, inv.data(), inv.size() * sizeof(int64_t), &d_inv));
+    AB_TRY(matrix_new(h, n, n, &K));
+    const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(n));
+    unpermute_kernel<<<grid, 256, 0, h->stream>>>(S->d, S->ld, static_cast<int64_t *>(d_inv), n, K->d, K->ld);
+    h->launches++;
+    AB_CUDA(cudaStreamSynchronize(h->stream)); // `inv` is a stack temporary
+    status = factorize(h, K, &f);             // consumes K
+    if (status != AB_OK) {
+      delete_factor(h, f);
+      return status;
+    }
+  }
+  phase_end(h, PH_FACTOR);
+  cudaEventRecord(h->ev_total_end, h->stream);
+  AB_CUDA(cudaStreamSynchronize(h->stream));
+  *out = f;
+  return AB_OK;
+}
+
 int ab_factor_sqrt_transpose(ab_handle h, ab_factor f, double *out) {
   AB_REQUIRE(h != nullptr && out != nullptr, "null");
   Lock lock(h);
@@ -849,6 +972,10 @@ int ab_gp_update(ab_handle h, ab_factor old_factor, const ab_op *prog, int nops,
   }
   phase_end(h, PH_GRAM);
   phase_begin(h, PH_FACTOR);
+  // pivot floor of the new block from its diagonal BEFORE the Schur complement is formed (linalg.cu potrf)
+  void *d_floor = nullptr;
+  AB_TRY(sc.alloc(static_cast<size_t>(p) * sizeof(double), &d_floor));
+  AB_TRY(pivot_floor(h, view(Cn), p, static_cast<double *>(d_floor)));
   // X = L^-1 B, in place;  S = C - X^T X (lower)
   AB_TRY(trsm_left_lower(h, view(old_factor->m), old_factor->dinv, n, view(B), p));
   AB_TRY(gemm(h, GEMM_TRANS_A | GEMM_LOWER, p, p, n, -1., view(B), view(B), 1., view(Cn)));
@@ -880,7 +1007,8 @@ int ab_gp_update(ab_handle h, ab_factor old_factor, const ab_op *prog, int nops,
   h->h_flags[0] = INT_MAX;
   if (status == AB_OK) {
     cudaMemcpyAsync(h->d_flags, h->h_flags, sizeof(int), cudaMemcpyHostToDevice, h->stream);
-    status = potrf(h, view(Lnew).sub(n, n), p, static_cast<double *>(tmp_inv), h->d_flags);
+    status = potrf(h, view(Lnew).sub(n, n), p, static_cast<double *>(tmp_inv), h->d_flags,
+                   static_cast<double *>(d_floor));
   }
   if (status == AB_OK) {
     leaf_inverse_kernel<<<static_cast<unsigned>((N + LEAF - 1) / LEAF), LEAF, 0, h->stream>>>(Lnew->d, Lnew->ld, N,

@@ -21,7 +21,8 @@ namespace ab {
 constexpr int LS = LEAF + 1; // padded shared-memory stride
 
 __global__ void __launch_bounds__(256)
-potf2_inv_kernel(double *A, int64_t lda, int nb, double *dinv, int64_t global_offset, int *d_bad) {
+potf2_inv_kernel(double *A, int64_t lda, int nb, double *dinv, int64_t global_offset, int *d_bad,
+                 const double *floor) {
   extern __shared__ double sm[];
   double *s = sm;               // s[r * LS + c]  : the block, lower triangle becomes L
   double *inv = sm + LEAF * LS; // inv[r * LS + c]: L^-1
@@ -41,7 +42,7 @@ potf2_inv_kernel(double *A, int64_t lda, int nb, double *dinv, int64_t global_of
   for (int j = 0; j < LEAF; ++j) {
     if (tid == 0) {
       const double d = s[j * LS + j];
-      if (!(d > 0.) && j < nb) {
+      if (j < nb && !(d > (floor != nullptr ? floor[j] : 0.))) {
         atomicMin(d_bad, static_cast<int>(global_offset + j));
       }
       s[j * LS + j] = sqrt(d);
@@ -105,7 +106,7 @@ potf2_inv_kernel(double *A, int64_t lda, int nb, double *dinv, int64_t global_of
 // LDS + reciprocal + 16 FMA) ~ 6 us.
 __global__ void __launch_bounds__(256)
 potf2_inv_kernel_v2(double *A, int64_t lda, int nb, double *dinv, int64_t global_offset,
-                    int *d_bad) {
+                    int *d_bad, const double *floor) {
   __shared__ double colbuf[2][LEAF];
   __shared__ double rowbuf[2][LEAF];
   __shared__ double dpiv[LEAF];
@@ -144,7 +145,9 @@ potf2_inv_kernel_v2(double *A, int64_t lda, int nb, double *dinv, int64_t global
     const double d = col[j];
     if (tid == 0) {
       dpiv[j] = d;
-      if (!(d > 0.) && j < nb) {
+      // a pivot must clear a floor relative to the ORIGINAL diagonal entry (see potrf): "> 0" alone lets a
+      // numerically singular matrix through whenever cancellation leaves +1e-17 instead of -1e-17
+      if (j < nb && !(d > (floor != nullptr ? floor[j] : 0.))) {
         atomicMin(d_bad, static_cast<int>(global_offset + j));
       }
     }
@@ -313,8 +316,9 @@ int trmm_left_lower(ab_handle_s *h, MatView L, int64_t n, bool trans, MatView X,
   return gemm(h, GEMM_TRANS_A, n1, p, n2, 1., L.sub(n1, 0), X.sub(n1, 0), 1., Y);
 }
 
+// floor: per-pivot thresholds of THIS sub-problem (may be null = 0)
 static int potrf_rec(ab_handle_s *h, MatView A, int64_t n, double *dinv, int64_t offset,
-                     int *d_bad) {
+                     int *d_bad, const double *floor) {
   if (n <= LEAF) {
     constexpr size_t smem = 2 * LEAF * LS * sizeof(double);
     static PerDeviceOnce once;
@@ -324,21 +328,22 @@ static int potrf_rec(ab_handle_s *h, MatView A, int64_t n, double *dinv, int64_t
     }
 #ifdef AB_LEAF_V1
     potf2_inv_kernel<<<1, 256, smem, h->stream>>>(A.p, A.ld, static_cast<int>(n), dinv, offset,
-                                                  d_bad);
+                                                  d_bad, floor);
 #else
     potf2_inv_kernel_v2<<<1, 256, 0, h->stream>>>(A.p, A.ld, static_cast<int>(n), dinv, offset,
-                                                  d_bad);
+                                                  d_bad, floor);
 #endif
     AB_LAUNCHED(h);
     return AB_OK;
   }
   const int64_t n1 = split(n);
   const int64_t n2 = n - n1;
-  AB_TRY(potrf_rec(h, A, n1, dinv, offset, d_bad));
+  AB_TRY(potrf_rec(h, A, n1, dinv, offset, d_bad, floor));
   AB_TRY(trsm_right_lower_T(h, A, dinv, n1, A.sub(n1, 0), n2));
   AB_TRY(gemm(h, GEMM_TRANS_B | GEMM_LOWER, n2, n2, n1, -1., A.sub(n1, 0), A.sub(n1, 0), 1.,
               A.sub(n1, n1)));
-  return potrf_rec(h, A.sub(n1, n1), n2, dinv + (n1 / LEAF) * LEAF * LEAF, offset + n1, d_bad);
+  return potrf_rec(h, A.sub(n1, n1), n2, dinv + (n1 / LEAF) * LEAF * LEAF, offset + n1, d_bad,
+                   floor != nullptr ? floor + n1 : nullptr);
 }
 
 // Right-looking blocked Cholesky with look-ahead 1 on two streams.
@@ -384,10 +389,10 @@ struct StreamScope {
 };
 
 static int factor_panel(ab_handle_s *h, MatView A, int64_t n, int64_t k0, int64_t w, double *dinv,
-                        int *d_bad) {
+                        int *d_bad, const double *floor) {
   StreamScope scope(h, h->panel_stream);
   double *dk = dinv + (k0 / LEAF) * LEAF * LEAF;
-  AB_TRY(potrf_rec(h, A.sub(k0, k0), w, dk, k0, d_bad));
+  AB_TRY(potrf_rec(h, A.sub(k0, k0), w, dk, k0, d_bad, floor != nullptr ? floor + k0 : nullptr));
   const int64_t below = n - k0 - w;
   if (below > 0) {
     AB_TRY(trsm_right_lower_T(h, A.sub(k0, k0), dk, w, A.sub(k0 + w, k0), below));
@@ -396,13 +401,14 @@ static int factor_panel(ab_handle_s *h, MatView A, int64_t n, int64_t k0, int64_
   return AB_OK;
 }
 
-static int potrf_lookahead(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad) {
+static int potrf_lookahead(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad,
+                           const double *floor) {
   AB_TRY(ensure_panel_stream(h));
   cudaStream_t S = h->stream;
   // the panel stream starts behind everything already enqueued on S (the Gram build of A)
   AB_CUDA(cudaEventRecord(h->ev_col, S));
   AB_CUDA(cudaStreamWaitEvent(h->panel_stream, h->ev_col, 0));
-  int status = factor_panel(h, A, n, 0, std::min(LA_NB, n), dinv, d_bad);
+  int status = factor_panel(h, A, n, 0, std::min(LA_NB, n), dinv, d_bad, floor);
   for (int64_t k0 = 0; status == AB_OK && k0 + LA_NB < n; k0 += LA_NB) {
     const int64_t w = LA_NB;
     const int64_t next = k0 + w;
@@ -422,7 +428,7 @@ static int potrf_lookahead(ab_handle_s *h, MatView A, int64_t n, double *dinv, i
     AB_CUDA(cudaEventRecord(h->ev_col, S));
     AB_CUDA(cudaStreamWaitEvent(h->panel_stream, h->ev_col, 0));
     // ... so that its factorisation overlaps the rest of this update
-    status = factor_panel(h, A, n, next, wn, dinv, d_bad);
+    status = factor_panel(h, A, n, next, wn, dinv, d_bad, floor);
     if (status == AB_OK && rest > 0) {
       const MatView Pr = A.sub(next + wn, k0);
       status = gemm(h, GEMM_TRANS_B | GEMM_LOWER, rest, rest, w, -1., Pr, Pr, 1.,
@@ -434,21 +440,63 @@ static int potrf_lookahead(ab_handle_s *h, MatView A, int64_t n, double *dinv, i
   return status;
 }
 
-int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad) {
+// floor[i] = PIVOT_RTOL * A(i, i)
+constexpr double PIVOT_RTOL = 64. * 2.220446049250313e-16;
+__global__ void pivot_floor_kernel(const double *A, int64_t ld, int64_t n, double *floor) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    floor[i] = PIVOT_RTOL * A[i + i * ld];
+  }
+}
+
+int pivot_floor(ab_handle_s *h, MatView A, int64_t n, double *d_floor) {
+  if (n <= 0) {
+    return AB_OK;
+  }
+  pivot_floor_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, h->stream>>>(A.p, A.ld, n, d_floor);
+  AB_LAUNCHED(h);
+  return AB_OK;
+}
+
+int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad, const double *d_floor) {
   if (n <= 0) {
     return AB_OK;
   }
   AB_REQUIRE(n < INT_MAX, "matrix too large");
+  // Pivot floor.  An unpivoted factorisation of a numerically singular matrix (duplicate points without a
+  // noise term) does not reliably meet a pivot <= 0: exact cancellation leaves +-1e-17, and a tiny POSITIVE
+  // pivot lets the factorisation "succeed" with garbage.  The reference's pivoted LDLT ends with (near) zero
+  // pivots that its callers see through is_positive_definite() / log_determinant().  Here a pivot must exceed
+  // 64 eps times the diagonal entry the matrix had BEFORE elimination, else AB_ERR_NOT_PD (condition numbers
+  // beyond ~1e13 are rejected rather than answered with noise).  Callers that factor a block which was already
+  // updated (dist.cu, ab_gp_update) pass the floor of the original diagonal.
+  void *own = nullptr;
+  const size_t bytes = static_cast<size_t>(n) * sizeof(double);
+  if (d_floor == nullptr) {
+    AB_TRY(dev_alloc(h, bytes, &own));
+    int s = pivot_floor(h, A, n, static_cast<double *>(own));
+    if (s != AB_OK) {
+      dev_release(h, own, bytes);
+      return s;
+    }
+    d_floor = static_cast<double *>(own);
+  }
   // AB_POTRF_RECURSIVE / AB_POTRF_LOOKAHEAD_MIN: test hooks (tests/test_gpu_gp.py compares the two
   // schedules at sizes below the default threshold)
   int64_t min_n = LA_MIN_N;
   if (const char *e = std::getenv("AB_POTRF_LOOKAHEAD_MIN")) {
     min_n = std::atoll(e);
   }
+  int status;
   if (n >= min_n && std::getenv("AB_POTRF_RECURSIVE") == nullptr) {
-    return potrf_lookahead(h, A, n, dinv, d_bad);
+    status = potrf_lookahead(h, A, n, dinv, d_bad, d_floor);
+  } else {
+    status = potrf_rec(h, A, n, dinv, 0, d_bad, d_floor);
   }
-  return potrf_rec(h, A, n, dinv, 0, d_bad);
+  if (own != nullptr) {
+    dev_release(h, own, bytes); // stream-ordered reuse: later users are enqueued behind the factorisation
+  }
+  return status;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -48,7 +48,11 @@ int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, dou
 // explicit inverses of the LEAF x LEAF diagonal blocks of L (block j at dinv + j*LEAF*LEAF,
 // column-major LEAF x LEAF, upper triangle zero).  d_bad: device int, atomicMin'ed with the global
 // index of the first non-positive pivot (initialise to INT_MAX).
-int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad);
+// d_floor (optional, n doubles on the device): pivot i is accepted only if it exceeds d_floor[i]; default:
+// 64 eps times the diagonal of A as passed in (pivot_floor).  Callers that factor an already-updated block
+// pass the floor of its ORIGINAL diagonal.
+int potrf(ab_handle_s *h, MatView A, int64_t n, double *dinv, int *d_bad, const double *d_floor = nullptr);
+int pivot_floor(ab_handle_s *h, MatView A, int64_t n, double *d_floor);
 
 // Creates (once) the handle's high-priority panel stream used by the look-ahead factorisations.
 int ensure_panel_stream(ab_handle_s *h);

@@ -609,7 +609,7 @@ def run_device_dist(args):
     n = args.dist_n
     # preflight (rank-symmetric, before any collective of the library): the block-column-cyclic shard, the
     # two packed panel buffers and 6 GB of slack must fit the free HBM of every rank, else halve N
-    nb_eff = args.nb or 1024
+    nb_eff = args.nb or (512 if world >= 4 else 1024)  # the library's default block-column width
     while n > 8192:
         nblk = (n + nb_eff - 1) // nb_eff
         need = 8.0 * n * ((nblk + world - 1) // world) * nb_eff + 2 * 8.0 * n * nb_eff + 6e9
@@ -702,7 +702,7 @@ def run_device_dist(args):
                                    "leg): one matrix, block-column-cyclic over the ranks, NCCL "
                                    "panel broadcasts; two Gram builds + two factorisations per step",
                        "flops_per_step": "2*N^3/3", "parallelism": f"block-cyclic 1x{world}, "
-                                                                   f"nb={args.nb or 1024}",
+                                                                   f"nb={nb_eff}, decoupled panel pipeline",
                        "l2_policy": "inputs (matrix shard >= 17 GB) larger than L2",
                        "scaling_note": "total work fixed for N_gpus = 2/4/8; the 1-GPU line is "
                                        "N=65536 (the same metric, FLOP/s, on 1/8 of the flops)"},

@@ -194,6 +194,17 @@ AB_API int ab_factor_inverse_blocks(ab_handle h, ab_factor f, const int64_t *ind
  */
 AB_API int ab_factor_export_packed(ab_handle h, ab_factor f, double *LD, int64_t *transpositions);
 
+/*
+ * The reverse: a device factor from Eigen::SerializableLDLT's packed form — what the reference's cereal
+ * archives hold (src/cereal/serializable_ldlt.hpp:18-32: the lower triangle with unit L below the diagonal and
+ * D on it, and the transpositions; src/cereal/gp.hpp:28-52 stores it inside Fit<GPFit>) — so that a fit
+ * serialised by the reference can be loaded onto the GPU.  LD: n x n column-major (only i >= j is read).
+ * Identity transpositions (every archive written from a device fit via ab_factor_export_packed): O(n^2).
+ * Otherwise K = P^T L D L^T P is rebuilt on the device (one DSYRK) and factored without pivoting.
+ * AB_ERR_NOT_PD when some D_ii <= 0.
+ */
+AB_API int ab_factor_import_packed(ab_handle h, const double *LD, const int64_t *transpositions, int64_t n,
+                            ab_factor *out);
 /* out = P^T L D^1/2 rhs = L_chol rhs.  SerializableLDLT::sqrt_product, serializable_ldlt.hpp:91-94. */
 AB_API int ab_factor_sqrt_product(ab_handle h, ab_factor f, const double *rhs, int64_t nrhs, double *out);
 /* out = P^T L^-T D^-1/2 rhs = L_chol^-T rhs.  sqrt_transpose_solve, serializable_ldlt.hpp:123-126. */

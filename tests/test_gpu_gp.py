@@ -368,7 +368,10 @@ def test_singular_psd_policy_next_to_the_reference(handle, golden):
     # what the device does
     f = handle.potrf(handle.upload(A), allow_not_pd=True)
     assert not f.is_positive_definite()
-    assert f.info() == 3            # x[3] duplicates x[2]: the first pivot that is not positive
+    # x[3] duplicates x[2]: exact cancellation leaves a pivot of +-1e-17 or 0 there; the factorisation accepts
+    # a pivot only above 64 eps times the original diagonal entry, so the singularity is caught AT pivot 3
+    # whatever the sign of the rounding noise (a bare "> 0" test would let +1e-17 through and return garbage)
+    assert f.info() == 3
     with pytest.raises(capi.AbError) as err:
         f.solve(rhs)
     assert err.value.status == 4    # AB_ERR_NOT_PD
@@ -413,3 +416,35 @@ def test_update_equals_full_fit(handle, n, p):
         fa, ia = handle.gp_update(f0, ops, pp, x[:n], info0, x[n:n + half], y[n:n + half], yvar_new=yvar[n:n + half])
         fb, ib = handle.gp_update(fa, ops, pp, x[:n + half], ia, x[n + half:], y[n + half:], yvar_new=yvar[n + half:])
         assert_close(ib, want, RTOL, "two chained updates")
+
+
+# ---- on-disk interoperability: the packed LDLT the reference's cereal archives hold (§8f-3) ---------------
+
+@pytest.mark.parametrize("n", [1, 64, 129, 500])
+def test_import_packed_roundtrip_and_pivoted_reference_factor(handle, n):
+    """ab_factor_import_packed: (i) export -> import of a device factor is bit-identical in every use;
+    (ii) the PIVOTED packed factor + transpositions the reference's LDLT produces (what
+    src/cereal/serializable_ldlt.hpp:18-32 writes) loads onto the device and solves like the reference."""
+    A = spd(n, seed=31 * n + 7)
+    scale = np.random.default_rng(n + 1).uniform(0.5, 2.0, size=n)   # unequal diagonal: the reference pivots
+    A = A * scale[:, None] * scale[None, :]
+    rhs = np.random.default_rng(n).standard_normal((n, 2))
+    f = handle.potrf(handle.upload(A))
+    LD, tr = f.export_packed()
+    g = handle.import_packed(LD, tr)
+    assert g.is_positive_definite() and g.n == n
+    assert_close(g.solve(rhs), f.solve(rhs), 1e-13, "export -> import solve")
+    assert abs(g.log_determinant() - f.log_determinant()) <= 1e-12 * max(1.0, abs(f.log_determinant()))
+    # the reference's own factor: pivoted, with non-trivial transpositions
+    ref = Restate.ldlt(A, rhs=rhs)
+    h2 = handle.import_packed(ref["ldlt"], ref["transpositions"])
+    assert_close(h2.solve(rhs), ref["solve"], RTOL, "solve from the reference's packed factor")
+    assert abs(h2.log_determinant() - ref["logdet"]) <= RTOL * max(1.0, abs(ref["logdet"]))
+    if n > 1:
+        assert np.any(ref["transpositions"] != np.arange(n)) or n < 3  # the pivoted path was exercised
+    # a non-positive D is rejected
+    bad = LD.copy()
+    bad[n // 2, n // 2] = -1.0
+    with pytest.raises(capi.AbError) as err:
+        handle.import_packed(bad, tr)
+    assert err.value.status == 4
