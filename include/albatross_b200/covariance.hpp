@@ -409,6 +409,23 @@ public:
   Parameter sigma_independent_noise;
 };
 
+// nugget_sigma^2 iff x == y, for any feature type with a device form, nugget.hpp:32-49 (fixed prior, 1e-8 by
+// default).  On the device it is the value-equality leaf of IndependentNoise.
+class Nugget : public CovarianceFunction<Nugget> {
+public:
+  static constexpr double default_nugget_noise = 1e-8; // nugget.hpp:16
+  Nugget() { nugget_sigma = {default_nugget_noise, FixedPrior()}; }
+  std::string name() const { return "nugget"; }
+  ALBATROSS_B200_PARAMS_1(nugget_sigma)
+  template <typename X, typename Y> static constexpr bool defined() {
+    return std::is_same<X, Y>::value && device_feature<X>::value;
+  }
+  template <typename X, typename Y> void emit(Program *prog, bool) const {
+    push_op(prog, AB_OP_INDEPENDENT_NOISE, nugget_sigma.value);
+  }
+  Parameter nugget_sigma;
+};
+
 /*
  * MeasurementOnly<Sub>, measurement.hpp:70-114: Sub between two Measurement<>s, exactly 0 otherwise.
  * The zero is emitted as a Constant with sigma 0 (0 * 0 = +0), so sums and products that contain it

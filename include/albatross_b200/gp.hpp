@@ -37,6 +37,30 @@ struct ZeroMean : public ParameterHandling<ZeroMean> {
   template <typename X> double call(const X &) const { return 0.; }
 };
 
+// slope * x + offset on scalar features, polynomials.hpp:93-108 (Gaussian(0, 1000) priors).  Mean functions stay
+// on the host: they are subtracted from the targets before the device fit and added to the predicted means.
+struct LinearMean : public ParameterHandling<LinearMean> {
+  LinearMean() {
+    slope = {0., GaussianPrior(0., 1000.)};
+    offset = {0., GaussianPrior(0., 1000.)};
+  }
+  std::string get_name() const { return "linear"; }
+  ParameterStore get_params() const { return {{"slope", slope}, {"offset", offset}}; }
+  void set_param(const ParameterKey &name, const Parameter &param) {
+    if (name == "slope") {
+      slope = param;
+    } else if (name == "offset") {
+      offset = param;
+    } else {
+      assert(false && "unknown parameter");
+    }
+  }
+  bool has_param(const ParameterKey &name) const { return name == "slope" || name == "offset"; }
+  double call(const double &x) const { return slope.value * x + offset.value; }
+  template <typename X> double call(const Measurement<X> &x) const { return call(x.value); }
+  Parameter slope, offset;
+};
+
 template <typename MeanFunc, typename X>
 inline void remove_mean(const MeanFunc &mean_function, const std::vector<X> &features, VectorXd *y) {
   if (std::is_same<MeanFunc, ZeroMean>::value) {

@@ -546,6 +546,45 @@ static void scenario_update() {
   dump("update.marginal", updated.predict(test).marginal());
 }
 
+static void scenario_nugget_and_linear_mean() {
+  // §8f-4: Nugget (nugget.hpp:32-49) and LinearMean (polynomials.hpp:93-108) in the layer
+  ab::Nugget nugget;
+  EXPECT(nugget.get_name() == "nugget" && nugget.get_params().at("nugget_sigma").value == 1e-8);
+  EXPECT(nugget.get_params().at("nugget_sigma").is_fixed());
+  auto data = make_1d(400, 17, 0., 10.);
+  nugget.set_param_value("nugget_sigma", 0.3);
+  ab::IndependentNoise<double> noise(0.3);
+  auto cov_n = SE(1.4, 1.2) + nugget;
+  auto cov_i = SE(1.4, 1.2) + noise;
+  const MatrixXd Kn = cov_n(data.features), Ki = cov_i(data.features);
+  EXPECT(Kn == Ki); // the same device leaf
+  // a linear trend handled by the mean function: y' = y + 0.7 x + 2 with LinearMean(0.7, 2) == y with ZeroMean
+  ab::LinearMean mean;
+  mean.set_param_value("slope", 0.7);
+  mean.set_param_value("offset", 2.);
+  VectorXd y2(data.targets.mean);
+  for (Index i = 0; i < y2.size(); ++i) {
+    y2[i] += 0.7 * data.features[static_cast<std::size_t>(i)] + 2.;
+  }
+  auto model_z = ab::gp_from_covariance(cov_i);
+  auto model_l = ab::gp_from_covariance_and_mean(cov_i, mean);
+  EXPECT(model_l.get_params().count("slope") == 1 && model_l.get_params().count("offset") == 1);
+  const auto fit_z = model_z.fit(data);
+  const auto fit_l = model_l.fit(ab::RegressionDataset<double>(data.features, y2));
+  double worst = 0.;
+  for (Index i = 0; i < y2.size(); ++i) {
+    worst = std::max(worst, std::fabs(fit_z.get_fit().information[i] - fit_l.get_fit().information[i]));
+  }
+  EXPECT(worst <= 1e-9);
+  std::vector<double> test = ab::linspace(0.5, 9.5, 7);
+  const VectorXd mz = fit_z.predict(test).mean(), ml = fit_l.predict(test).mean();
+  for (Index i = 0; i < mz.size(); ++i) {
+    EXPECT(std::fabs(ml[i] - (mz[i] + 0.7 * test[static_cast<std::size_t>(i)] + 2.)) <= 1e-9);
+  }
+  EXPECT(std::fabs(model_l.log_likelihood(ab::RegressionDataset<double>(data.features, y2)) -
+                   model_l.prior_log_likelihood() - (model_z.log_likelihood(data) - model_z.prior_log_likelihood())) <= 1e-7);
+}
+
 static void scenario_not_positive_definite() {
   // Duplicate points without a noise term: K is singular.  The reference's pivoted LDLT proceeds and its
   // outputs are NaN / inf (GenericTuner maps a NaN objective to +inf, tune.hpp:164-166); the device reports
@@ -596,6 +635,7 @@ int main(int argc, char **argv) {
       scenario_block_diagonal_and_qr();
       scenario_tuner();
       scenario_update();
+      scenario_nugget_and_linear_mean();
       const ab_phase_times t = ab::Device::default_device()->timings();
       dump("kernel_launches", static_cast<double>(t.kernel_launches));
     } catch (const ab::device_error &e) {

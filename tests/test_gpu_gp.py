@@ -378,10 +378,15 @@ def test_singular_psd_policy_next_to_the_reference(handle, golden):
     with pytest.raises(capi.AbError) as err:
         handle.gp_nll([capi.SE], [1.0, 1.0], ref["psd_x"], rhs)
     assert err.value.status == 4
-    # a noise term (the case every shipped model has) makes the same data positive definite on both sides
+    # IndependentNoise is value equality (noise.hpp:37-43): duplicated features share it, K stays singular
     ops, pp = prog(6)
-    want = Restate.gp_nll(ops, pp, ref["psd_x"], rhs)
-    assert abs(handle.gp_nll(ops, pp, ref["psd_x"], rhs) - want) <= RTOL * abs(want)
+    with pytest.raises(capi.AbError):
+        handle.gp_nll(ops, pp, ref["psd_x"], rhs)
+    # measurement variance on the targets (gp.hpp:65) is per observation: the fit is positive definite on both sides
+    yvar = np.full(len(rhs), 0.01)
+    f2, info = handle.gp_fit(ops, pp, ref["psd_x"], rhs, yvar=yvar)
+    assert f2.is_positive_definite()
+    assert_close(info, Restate.gp_fit(ops, pp, ref["psd_x"], rhs, yvar=yvar)["information"], RTOL, "fit with yvar")
 
 
 # ---- incremental update (tests/test_gp.cc:182-219: a partial fit followed by update == a full fit) ----
