@@ -612,9 +612,51 @@ static void scenario_not_positive_definite() {
   }
 }
 
+// host-only checks of the tuner front and the QR helpers (no device call)
+static void host_checks_tune_and_linalg() {
+  // bounded Nelder-Mead on a shifted quadratic with a minimum outside the box on one axis
+  auto f = [](const std::vector<double> &x) { return (x[0] - 1.5) * (x[0] - 1.5) + 3. * (x[1] + 4.) * (x[1] + 4.) + 2.; };
+  const ab::SimplexResult r = ab::minimize_simplex(f, {0., 0.}, {-1., -2.}, {5., 5.});
+  EXPECT(std::fabs(r.x[0] - 1.5) < 1e-3 && std::fabs(r.x[1] + 2.) < 1e-9); // x1 clamped to its lower bound
+  EXPECT(std::fabs(r.f - (2. + 3. * 4.)) < 1e-5 && r.evaluations < 2000);
+  // NaN objectives are +inf (tune.hpp:164-166): the simplex walks away from them
+  auto g = [](const std::vector<double> &x) { return x[0] < 0.5 ? std::nan("") : (x[0] - 2.) * (x[0] - 2.); };
+  const ab::SimplexResult r2 = ab::minimize_simplex(g, {1.}, {0.}, {4.});
+  EXPECT(std::fabs(r2.x[0] - 2.) < 1e-3);
+  // finite differences, vector form (finite_difference.hpp:18-32), dealt over 3 lanes
+  auto q = [](const std::vector<double> &x) { return x[0] * x[0] + 3. * x[1] - x[2] * x[2] * x[2]; };
+  const std::vector<double> x0 = {1., 2., 0.5};
+  const std::vector<double> grad = ab::compute_gradient(q, x0, q(x0), 3);
+  EXPECT(std::fabs(grad[0] - 2.) < 1e-5 && std::fabs(grad[1] - 3.) < 1e-5 && std::fabs(grad[2] + 0.75) < 1e-5);
+  // ParameterStore form: log-scale priors are stepped in log space, fixed parameters are skipped
+  ab::ParameterStore ps;
+  ps["a"] = {2., ab::PositivePrior()};
+  ps["b"] = {3., ab::FixedPrior()};
+  auto pf = [](const ab::ParameterStore &p) { return p.at("a").value * p.at("a").value + p.at("b").value; };
+  const std::vector<double> pg = ab::compute_gradient(pf, ps, pf(ps));
+  EXPECT(pg.size() == 1 && std::fabs(pg[0] - 4.) < 1e-4);
+  // GenericTuner over a ParameterStore objective
+  std::ostringstream log;
+  ab::GenericTuner tuner(ps, log);
+  auto obj = [](const ab::ParameterStore &p) { return (p.at("a").value - 0.7) * (p.at("a").value - 0.7); };
+  const ab::ParameterStore tuned = tuner.tune(obj);
+  EXPECT(std::fabs(tuned.at("a").value - 0.7) < 1e-3 && tuned.at("b").value == 3.);
+  // sqrt_solve(R, P, rhs) = R^-T P^T rhs (qr_utils.hpp:35-45)
+  MatrixXd R(3, 3);
+  R(0, 0) = 2.; R(0, 1) = 1.; R(0, 2) = -1.;
+  R(1, 0) = 0.; R(1, 1) = 3.; R(1, 2) = 0.5;
+  R(2, 0) = 0.; R(2, 1) = 0.; R(2, 2) = 4.;
+  MatrixXd rhs(3, 1);
+  rhs(0, 0) = 4.; rhs(1, 0) = 5.; rhs(2, 0) = 6.;
+  const MatrixXd z = ab::sqrt_solve(R, std::vector<Index>{2, 0, 1}, rhs); // P^T rhs = (6, 4, 5)
+  EXPECT(std::fabs(z(0, 0) - 3.) < 1e-15 && std::fabs(z(1, 0) - (4. - 1. * 3.) / 3.) < 1e-15);
+  EXPECT(std::fabs(z(2, 0) - (5. + 3. - 0.5 * (1. / 3.)) / 4.) < 1e-15);
+}
+
 int main(int argc, char **argv) {
   if (argc >= 2 && std::strcmp(argv[1], "host") == 0) {
     host_checks();
+    host_checks_tune_and_linalg();
     std::printf("trait_layer_check host: %d failure(s)\n", failures);
     return failures == 0 ? 0 : 1;
   }

@@ -119,3 +119,34 @@ def test_loo_shards_sum_to_full(handle):
     assert_close(vs, var, 1e-10)
     assert abs(ss - score) <= 1e-10 * abs(score)
     f.free()
+
+
+def test_world1_broadcast_and_breakdown(handle):
+    """ab_dist_factor_broadcast is the identity on a one-rank group; ab_dist_fit_breakdown reports the per-step
+    accounting of the most recent distributed fit (the decoupled panel pipeline also runs without NCCL)."""
+    ops, pp = prog(8)
+    x = features(2300, 3, 4)
+    y = targets(x)
+    f, info = handle.gp_fit(ops, pp, x, y)
+    g = handle.dist_factor_broadcast(f, root=0)
+    assert g is f
+    df, dinfo, nll = handle.dist_gp_fit(ops, pp, x, y, nb=256)
+    wait_ms, panel_ms, steps = handle.dist_fit_breakdown()
+    assert steps == 9 and wait_ms >= 0.0 and panel_ms > 0.0
+    assert_close(dinfo, info, 1e-10, "distributed (world 1, pipeline) vs single-GPU information")
+    df.free()
+
+
+@pytest.mark.parametrize("schedule", ["lookahead1", "pipeline"])
+def test_dist_schedules_agree(handle, schedule, monkeypatch):
+    """Both schedules of the distributed factorisation (AB_DIST_SCHEDULE) give the oracle's answer."""
+    if schedule == "lookahead1":
+        monkeypatch.setenv("AB_DIST_SCHEDULE", "lookahead1")
+    ops, pp = prog(6)
+    x = features(1700, 1, 9).ravel()
+    y = targets(x)
+    df, info, nll = handle.dist_gp_fit(ops, pp, x, y, nb=128)
+    assert_close(info, Restate.gp_fit(ops, pp, x, y)["information"], 1e-9, f"{schedule} information")
+    want = Restate.gp_nll(ops, pp, x, y)
+    assert abs(nll - want) <= 1e-9 * abs(want)
+    df.free()
