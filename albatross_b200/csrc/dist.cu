@@ -52,6 +52,7 @@ struct NcclApi {
   void *lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr; // optional
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
@@ -92,6 +93,8 @@ int load_nccl() {
   AB_NCCL_SYM(Broadcast, "ncclBroadcast")
   AB_NCCL_SYM(Reduce, "ncclReduce")
 #undef AB_NCCL_SYM
+  g_nccl.CommInitRankConfig =
+      reinterpret_cast<decltype(g_nccl.CommInitRankConfig)>(dlsym(lib, "ncclCommInitRankConfig"));
   g_nccl.lib = lib;
   return AB_OK;
 }
@@ -697,7 +700,21 @@ int ab_dist_init(ab_handle h, int rank, int world, const void *id) {
   ncclUniqueId uid;
   std::memcpy(&uid, id, sizeof(uid));
   ncclComm_t comm = nullptr;
-  AB_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+  // The panel broadcasts run WHILE the DMMA updates fill the machine: every NCCL CTA takes an SM's worth of
+  // shared memory from them.  Eight CTAs carry a 0.5-1 GB panel fast enough (N = 131 072 on 8 GPUs, same box:
+  // factorisation 3125 ms with NCCL's default, 3045 ms with 8 channels, 3094 ms with 4 where the chain starts to
+  // wait; profiles/r02o_*), so the communicator is capped at 8 (AB_DIST_NCCL_MAX_CTAS overrides; 0 = NCCL default).
+  int max_ctas = 8;
+  if (const char *e = std::getenv("AB_DIST_NCCL_MAX_CTAS")) {
+    max_ctas = std::atoi(e);
+  }
+  if (g_nccl.CommInitRankConfig != nullptr && max_ctas > 0) {
+    ncclConfig_t config = NCCL_CONFIG_INITIALIZER;
+    config.maxCTAs = max_ctas;
+    AB_NCCL(g_nccl.CommInitRankConfig(&comm, world, uid, rank, &config));
+  } else {
+    AB_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
+  }
   h->comm = comm;
   return ensure_dist_streams(h);
 }
