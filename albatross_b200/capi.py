@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ALBATROSS_B200_LIB") or os.path.join(HERE, "csrc", "libalbatross_b200.so")
 
 # opcodes (include/albatross_b200.h)
-SE, EXP, M32, M52, CONST, NOISE, SUM, PROD = 1, 2, 3, 4, 5, 6, 7, 8
+SE, EXP, M32, M52, CONST, NOISE, SUM, PROD, POLY = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 def bench_program(name):

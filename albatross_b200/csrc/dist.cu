@@ -603,7 +603,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
           d_y + r0, W > 1 ? t : pbuf, wj, zj);
       AB_LAUNCHED(h);
       const MatView D = colblk(j).sub(r0, 0);
-      AB_TRY(trsv_block(h, false, D, dinv_of(j), wj, zj));
+      AB_TRY(trsv_lower(h, D, dinv_of(j), wj, zj)); // 512-row sub-blocks: one CTA solving 1024 rows costs ~1 ms
       AB_CUDA(cudaMemcpyAsync(z + r0, zj, static_cast<size_t>(wj) * sizeof(double),
                               cudaMemcpyDeviceToDevice, h->stream));
       AB_TRY(logdet_chol(h, D, wj, static_cast<double *>(d_logs) + j));
@@ -623,7 +623,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
       sub_kernel<<<static_cast<unsigned>((wj + 255) / 256), 256, 0, h->stream>>>(
           zl + l * nb, tl + l * nb, wj, x + r0);
       AB_LAUNCHED(h);
-      AB_TRY(trsv_block(h, true, colblk(j).sub(r0, 0), dinv_of(j), wj, x + r0));
+      AB_TRY(trsv_lower_T(h, colblk(j).sub(r0, 0), dinv_of(j), wj, x + r0));
     }
     if (W > 1) {
       AB_NCCL(g_nccl.Broadcast(x + r0, x + r0, static_cast<size_t>(wj), ncclDouble, root, comm_of(h),

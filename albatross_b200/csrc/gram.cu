@@ -13,6 +13,9 @@
 // 10 FP64 ops, <= 1 ulp) and sqrt (MUFU.RSQ64H seed + Goldschmidt, 7 FP64 ops, <= 1 ulp).
 #include "gram_kernel.cuh"
 
+#include <algorithm>
+#include <vector>
+
 #include <cstring>
 
 #include <cmath>
@@ -88,7 +91,93 @@ static bool leaf_to_dev(const ab_op &o, DevOp *d) {
   return true;
 }
 
+static int compile_stationary(const ab_op *prog, int nops, DevProg *out);
+
+// Splits the top-level sum of the postfix program into its summands (index ranges of complete sub-programs).
+static bool top_level_summands(const ab_op *prog, int nops, std::vector<std::pair<int, int>> *terms) {
+  // span[k] = first index of the sub-expression that ends at k
+  std::vector<int> span(static_cast<size_t>(nops)), stack;
+  for (int k = 0; k < nops; ++k) {
+    if (prog[k].op == AB_OP_SUM || prog[k].op == AB_OP_PRODUCT) {
+      if (stack.size() < 2) {
+        return false;
+      }
+      stack.pop_back();
+      span[static_cast<size_t>(k)] = span[static_cast<size_t>(stack.back())];
+      stack.back() = k;
+    } else {
+      span[static_cast<size_t>(k)] = k;
+      stack.push_back(k);
+    }
+  }
+  if (stack.size() != 1) {
+    return false;
+  }
+  // walk down the SUM spine from the root
+  std::vector<int> todo = {nops - 1};
+  while (!todo.empty()) {
+    const int k = todo.back();
+    todo.pop_back();
+    if (prog[k].op == AB_OP_SUM) {
+      const int rhs_end = k - 1;
+      const int lhs_end = span[static_cast<size_t>(rhs_end)] - 1;
+      todo.push_back(rhs_end);
+      todo.push_back(lhs_end);
+    } else {
+      terms->emplace_back(span[static_cast<size_t>(k)], k);
+    }
+  }
+  std::sort(terms->begin(), terms->end());
+  return true;
+}
+
 int compile_program(const ab_op *prog, int nops, DevProg *out) {
+  AB_REQUIRE(prog != nullptr && nops >= 1 && nops <= AB_MAX_OPS, "covariance program size");
+  out->npoly = 0;
+  bool has_poly = false;
+  for (int k = 0; k < nops; ++k) {
+    has_poly = has_poly || prog[k].op == AB_OP_POLYNOMIAL_TERM;
+  }
+  if (!has_poly) {
+    return compile_stationary(prog, nops, out);
+  }
+  // polynomial terms must be summands of the top-level sum; everything else is compiled as before
+  std::vector<std::pair<int, int>> terms;
+  AB_REQUIRE(top_level_summands(prog, nops, &terms), "malformed postfix covariance program");
+  std::vector<ab_op> rest;
+  int nrest = 0, npoly = 0;
+  for (const auto &t : terms) {
+    if (t.first == t.second && prog[t.first].op == AB_OP_POLYNOMIAL_TERM) {
+      const double deg = prog[t.first].p1;
+      if (npoly >= AB_MAX_POLY || !(deg >= 0. && deg <= 16. && deg == std::floor(deg))) {
+        set_error("polynomial term: at most %d terms of integer degree 0..16", AB_MAX_POLY);
+        return AB_ERR_UNSUPPORTED;
+      }
+      out->poly_deg[npoly] = static_cast<int>(deg);
+      out->poly_s2[npoly] = prog[t.first].p0 * prog[t.first].p0;
+      ++npoly;
+      continue;
+    }
+    for (int k = t.first; k <= t.second; ++k) {
+      if (prog[k].op == AB_OP_POLYNOMIAL_TERM) {
+        set_error("a Polynomial term inside a product has no device form (only as a summand of the covariance)");
+        return AB_ERR_UNSUPPORTED;
+      }
+      rest.push_back(prog[k]);
+    }
+    if (nrest++ > 0) {
+      rest.push_back(ab_op{AB_OP_SUM, 0, 0., 0.});
+    }
+  }
+  if (rest.empty()) {
+    rest.push_back(ab_op{AB_OP_CONSTANT, 0, 0., 0.}); // a purely polynomial covariance: 0 + terms
+  }
+  AB_TRY(compile_stationary(rest.data(), static_cast<int>(rest.size()), out));
+  out->npoly = npoly;
+  return AB_OK;
+}
+
+static int compile_stationary(const ab_op *prog, int nops, DevProg *out) {
   AB_REQUIRE(prog != nullptr && nops >= 1 && nops <= AB_MAX_OPS, "covariance program size");
   // validate postfix shape
   int depth = 0, max_depth = 0;
@@ -238,9 +327,9 @@ __global__ void gram_diag_kernel(const __grid_constant__ DevProg P, const double
 }
 
 template <bool SYM>
-static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *fx, int64_t ldfx,
-                       int64_t n, const double *fy, int64_t ldfy, int64_t m, double *out,
-                       int64_t ld, uint32_t flags) {
+static int launch_gram_base(ab_handle_s *h, const DevProg &P, int dim, const double *fx, int64_t ldfx,
+                            int64_t n, const double *fy, int64_t ldfy, int64_t m, double *out,
+                            int64_t ld, uint32_t flags) {
   if (n == 0 || m == 0) {
     return AB_OK;
   }
@@ -303,6 +392,62 @@ static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *
 #undef AB_GRAM_CASE
   AB_CUDA(launch_err);
   h->launches++;
+  return AB_OK;
+}
+
+// out(i, j) += sum_p s2_p x_i^p y_j^p (scalar features).  sym: i >= j only, mirrored unless lower_only.
+__device__ __forceinline__ double poly_value(const DevProg &P, double x, double y) {
+  double v = 0.;
+  for (int t = 0; t < P.npoly; ++t) {
+    double xp = 1., yp = 1.;
+    for (int e = 0; e < P.poly_deg[t]; ++e) {
+      xp *= x;
+      yp *= y;
+    }
+    v += P.poly_s2[t] * xp * yp;
+  }
+  return v;
+}
+
+__global__ void poly_add_kernel(const __grid_constant__ DevProg P, const double *__restrict__ fx, int64_t ldfx,
+                                int64_t n, const double *__restrict__ fy, int64_t ldfy, int64_t m, double *out,
+                                int64_t ld, int sym, int lower_only) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t j = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;
+  if (i >= n || j >= m || (sym && i < j)) {
+    return;
+  }
+  const double v = poly_value(P, fx[i * ldfx], fy[j * ldfy]);
+  out[i + j * ld] += v;
+  if (sym && !lower_only && i != j) {
+    out[j + i * ld] += v;
+  }
+}
+
+__global__ void poly_add_diag_kernel(const __grid_constant__ DevProg P, const double *__restrict__ f, int64_t ldf,
+                                     int64_t n, double *out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    out[i] += poly_value(P, f[i * ldf], f[i * ldf]);
+  }
+}
+
+template <bool SYM>
+static int launch_gram(ab_handle_s *h, const DevProg &P, int dim, const double *fx, int64_t ldfx,
+                       int64_t n, const double *fy, int64_t ldfy, int64_t m, double *out,
+                       int64_t ld, uint32_t flags) {
+  AB_TRY((launch_gram_base<SYM>(h, P, dim, fx, ldfx, n, fy, ldfy, m, out, ld, flags)));
+  if (P.npoly > 0 && n > 0 && m > 0) {
+    if (dim != 1) {
+      set_error("Polynomial covariance terms are defined for scalar features (polynomials.hpp:79)");
+      return AB_ERR_UNSUPPORTED;
+    }
+    const dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(m < 65535 ? m : 65535),
+                    static_cast<unsigned>((m + 65534) / 65535));
+    poly_add_kernel<<<grid, 256, 0, h->stream>>>(P, fx, ldfx, n, fy, ldfy, m, out, ld, SYM ? 1 : 0,
+                                                 (flags & AB_GRAM_LOWER_ONLY) ? 1 : 0);
+    AB_LAUNCHED(h);
+  }
   return AB_OK;
 }
 
@@ -386,6 +531,14 @@ int gram_diag_device(ab_handle_s *h, const DevProg &P, const ab_matrix_s *feats,
   }
 #undef AB_DIAG_CASE
   AB_LAUNCHED(h);
+  if (P.npoly > 0) {
+    if (dim != 1) {
+      set_error("Polynomial covariance terms are defined for scalar features (polynomials.hpp:79)");
+      return AB_ERR_UNSUPPORTED;
+    }
+    poly_add_diag_kernel<<<grid, block, 0, h->stream>>>(P, feats->d, feats->ld, n, d_out);
+    AB_LAUNCHED(h);
+  }
   return AB_OK;
 }
 

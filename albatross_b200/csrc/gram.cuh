@@ -46,12 +46,20 @@ struct DevOp {
 //         right with two accumulators exactly as the reference's left-associated operator+/operator*
 //         tree would; no stack.
 // mode 1: generic postfix with an evaluation stack (any nesting).
+constexpr int AB_MAX_POLY = 8;
+
 struct DevProg {
   int nops;
   int mode;
   int need_dist;  // some leaf needs d = sqrt(d^2)
   int need_equal; // some leaf needs feature equality
   DevOp ops[AB_MAX_OPS];
+  // Polynomial terms sigma_p^2 x^p y^p (polynomials.hpp:63-90; scalar features) that stand as top-level
+  // summands of the covariance: not distance based, so they are added to the finished block by a second
+  // elementwise pass instead of going through the pairwise evaluator.
+  int npoly;
+  int poly_deg[AB_MAX_POLY];
+  double poly_s2[AB_MAX_POLY];
 };
 
 int compile_program(const ab_op *prog, int nops, DevProg *out);

@@ -63,7 +63,10 @@ typedef enum {
   AB_OP_CONSTANT = 5,            /* p0 = sigma                      src/covariance_functions/polynomials.hpp:56-60 */
   AB_OP_INDEPENDENT_NOISE = 6,   /* p0 = sigma; value equality      src/covariance_functions/noise.hpp:37-43 */
   AB_OP_SUM = 7,                 /* lhs + rhs                       covariance_function.hpp:270-272 */
-  AB_OP_PRODUCT = 8              /* lhs != 0 ? lhs * rhs : lhs      covariance_function.hpp:361-367 */
+  AB_OP_PRODUCT = 8,             /* lhs != 0 ? lhs * rhs : lhs      covariance_function.hpp:361-367 */
+  AB_OP_POLYNOMIAL_TERM = 9      /* p0 = sigma, p1 = degree p: sigma^2 x^p y^p, one term of Polynomial<order>
+                                    (polynomials.hpp:63-90; scalar features).  Only as a summand of the top-level
+                                    sum (AB_ERR_UNSUPPORTED inside a product). */
 } ab_opcode;
 
 typedef struct {

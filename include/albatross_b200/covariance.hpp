@@ -393,6 +393,63 @@ public:
   Parameter sigma_constant;
 };
 
+/*
+ * Polynomial<order>, polynomials.hpp:63-90: sum_p sigma_p^2 x^p y^p between two doubles, one parameter
+ * "sigma_polynomial_<p>" per degree.  On the device every degree is one AB_OP_POLYNOMIAL_TERM leaf; the
+ * Gram builder accepts them as summands of the top-level sum only (a product with a Polynomial has no
+ * device form: AB_ERR_UNSUPPORTED from the library, there is no CPU fallback).
+ */
+template <int order> class Polynomial : public CovarianceFunction<Polynomial<order>> {
+  static_assert(order >= 0 && order <= 7, "albatross_b200: Polynomial<order> carries at most 8 device terms");
+
+public:
+  Polynomial(double sigma = Constant::default_sigma) {
+    for (int i = 0; i <= order; ++i) {
+      sigmas_[static_cast<std::size_t>(i)] = {sigma, NonNegativePrior()};
+    }
+  }
+  std::string name() const { return "polynomial_" + std::to_string(order); }
+  static std::string param_name(int i) { return "sigma_polynomial_" + std::to_string(i); }
+  ParameterStore get_params() const {
+    ParameterStore out;
+    for (int i = 0; i <= order; ++i) {
+      out[param_name(i)] = sigmas_[static_cast<std::size_t>(i)];
+    }
+    return out;
+  }
+  bool has_param(const ParameterKey &name_) const {
+    for (int i = 0; i <= order; ++i) {
+      if (name_ == param_name(i)) {
+        return true;
+      }
+    }
+    return false;
+  }
+  void set_param(const ParameterKey &name_, const Parameter &p_) {
+    for (int i = 0; i <= order; ++i) {
+      if (name_ == param_name(i)) {
+        sigmas_[static_cast<std::size_t>(i)] = p_;
+        return;
+      }
+    }
+    assert(false && "unknown parameter");
+  }
+  template <typename X, typename Y> static constexpr bool defined() {
+    return std::is_same<X, double>::value && std::is_same<Y, double>::value;
+  }
+  template <typename X, typename Y> void emit(Program *prog, bool) const {
+    for (int i = 0; i <= order; ++i) {
+      push_op(prog, AB_OP_POLYNOMIAL_TERM, sigmas_[static_cast<std::size_t>(i)].value, static_cast<double>(i));
+      if (i > 0) {
+        push_op(prog, AB_OP_SUM);
+      }
+    }
+  }
+
+private:
+  std::array<Parameter, static_cast<std::size_t>(order + 1)> sigmas_;
+};
+
 // sigma^2 iff x == y, defined only between two `Observed`s, noise.hpp:20-45.
 template <typename Observed> class IndependentNoise : public CovarianceFunction<IndependentNoise<Observed>> {
 public:

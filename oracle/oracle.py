@@ -53,7 +53,7 @@ def build(target="all"):
 
 # Covariance menu of the compiled reference (oracle/ref_shim/ref_common.h); value = the equivalent
 # postfix program understood by the restatement and by the device (include/albatross_b200.h).
-SE, EXP, M32, M52, CONST, NOISE, SUM, PROD = 1, 2, 3, 4, 5, 6, 7, 8
+SE, EXP, M32, M52, CONST, NOISE, SUM, PROD, POLY = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 def menu_program(cov_id, p):
@@ -80,6 +80,11 @@ def menu_program(cov_id, p):
     if cov_id == 10:
         # SE + measurement_only(NOISE), as seen between two Measurement<> features (the fit)
         return [SE, NOISE, SUM], [p[0], p[1], p[2], 0.0, 0.0, 0.0]
+    if cov_id == 11:
+        # Polynomial<1> + SE + measurement_only(NOISE) between two Measurement<> features:
+        # ((t0 + t1) + SE) + NOISE, each polynomial term (sigma, degree)
+        return ([POLY, POLY, SUM, SE, SUM, NOISE, SUM],
+                [p[0], 0.0, p[1], 1.0, 0, 0, p[2], p[3], 0, 0, p[4], 0.0, 0, 0])
     raise ValueError(cov_id)
 
 
@@ -90,6 +95,9 @@ def menu_program_plain(cov_id, p):
     if cov_id == 10:
         p = list(map(float, p))
         return [SE], [p[0], p[1]]
+    if cov_id == 11:
+        p = list(map(float, p))
+        return [POLY, POLY, SUM, SE, SUM], [p[0], 0.0, p[1], 1.0, 0, 0, p[2], p[3], 0, 0]
     return menu_program(cov_id, p)
 
 

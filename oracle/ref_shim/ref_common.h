@@ -21,6 +21,8 @@
  *   8   SE + Matern52 + IndependentNoise                  [l1, s1, l2, s2, sn]
  *   9   SE*Matern32 + Exponential*Constant + Noise        [l1, s1, l2, s2, l3, s3, sc, sn]
  *   10  SE + measurement_only(IndependentNoise<X>)        [l, s, sn]   (examples/sinc_example.cc:79-80)
+ *   11  Polynomial<1> + SE + measurement_only(noise)      [s0, s1, l, s, sn]  (examples/sinc_example.cc:84-87;
+ *                                                          scalar features only)
  *
  * Feature types: dim==1 -> double, dim==3 -> Eigen::Vector3d, otherwise Eigen::VectorXd
  * (AoS doubles, point i at feats[i*dim .. i*dim+dim)).
@@ -50,6 +52,25 @@ using SE = SquaredExponential<EuclideanDistance>;
 using EXP = Exponential<EuclideanDistance>;
 using M32 = Matern32<EuclideanDistance>;
 using M52 = Matern52<EuclideanDistance>;
+
+/* Polynomial<1> with its two sigmas set (polynomials.hpp:63-90). */
+inline albatross::Polynomial<1> linear_polynomial(double s0, double s1) {
+  albatross::Polynomial<1> p;
+  p.set_param_value("sigma_polynomial_0", s0);
+  p.set_param_value("sigma_polynomial_1", s1);
+  return p;
+}
+
+/* Entry 11 exists for scalar features only (Polynomial is defined on double). */
+template <typename X, typename F> struct Entry11 {
+  static int call(const double *, F &&) { return -1; }
+};
+template <typename F> struct Entry11<double, F> {
+  static int call(const double *p, F &&f) {
+    f(linear_polynomial(p[0], p[1]) + SE(p[2], p[3]) + albatross::measurement_only(IndependentNoise<double>(p[4])));
+    return 0;
+  }
+};
 
 template <typename X> struct FeatureIO;
 
@@ -124,6 +145,8 @@ inline int with_cov(int cov_id, const double *p, F &&f) {
   case 10:
     f(SE(p[0], p[1]) + albatross::measurement_only(IndependentNoise<X>(p[2])));
     return 0;
+  case 11:
+    return Entry11<X, F>::call(p, std::forward<F>(f));
   default:
     return -1;
   }
@@ -146,6 +169,8 @@ inline int with_gp_cov(int cov_id, const double *p, F &&f) {
   case 10:
     f(SE(p[0], p[1]) + albatross::measurement_only(IndependentNoise<X>(p[2])));
     return 0;
+  case 11:
+    return Entry11<X, F>::call(p, std::forward<F>(f));
   default:
     return -1;
   }

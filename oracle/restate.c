@@ -111,6 +111,9 @@ double rs_cov_eval(const rs_op *prog, int nops, const double *x, const double *y
     case RS_OP_INDEPENDENT_NOISE:
       stack[sp++] = features_equal(x, y, dim) ? o->p0 * o->p0 : 0.;
       break;
+    case RS_OP_POLYNOMIAL_TERM: /* polynomials.hpp:79-87: sigma^2 pow(x, p) pow(y, p), scalar features */
+      stack[sp++] = o->p0 * o->p0 * pow(x[0], o->p1) * pow(y[0], o->p1);
+      break;
     case RS_OP_SUM: {
       const double rhs = stack[--sp];
       const double lhs = stack[--sp];

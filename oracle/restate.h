@@ -32,7 +32,8 @@ enum {
   RS_OP_CONSTANT = 5,          /* p0 = sigma */
   RS_OP_INDEPENDENT_NOISE = 6, /* p0 = sigma */
   RS_OP_SUM = 7,               /* pops rhs, lhs; pushes lhs + rhs */
-  RS_OP_PRODUCT = 8            /* pops rhs, lhs; pushes lhs != 0 ? lhs * rhs : lhs */
+  RS_OP_PRODUCT = 8,
+  RS_OP_POLYNOMIAL_TERM = 9 /* p0 = sigma, p1 = degree: one term of Polynomial<order>, polynomials.hpp:79-87 */            /* pops rhs, lhs; pushes lhs != 0 ? lhs * rhs : lhs */
 };
 
 typedef struct {

@@ -122,6 +122,21 @@ static void host_checks() {
                     ab::is_device_feature<M>::value && !ab::is_device_feature<std::string>::value,
                 "device feature trait");
 
+  // Polynomial<order> (polynomials.hpp:63-90): one parameter and one device term per degree, doubles only
+  ab::Polynomial<1> linear(100.);
+  EXPECT(linear.get_name() == "polynomial_1");
+  EXPECT(linear.get_params().size() == 2 && linear.get_param_value("sigma_polynomial_1") == 100.);
+  linear.set_param_value("sigma_polynomial_0", 3.);
+  auto sinc_cov = linear + se + ab::measurement_only(noise);
+  EXPECT(sinc_cov.get_params().size() == 5);
+  auto p_poly = sinc_cov.program<M, M>();
+  EXPECT(p_poly.size() == 7 && p_poly[0].op == AB_OP_POLYNOMIAL_TERM && p_poly[0].p0 == 3. && p_poly[0].p1 == 0. &&
+         p_poly[1].op == AB_OP_POLYNOMIAL_TERM && p_poly[1].p0 == 100. && p_poly[1].p1 == 1. &&
+         p_poly[2].op == AB_OP_SUM && p_poly[3].op == AB_OP_SQUARED_EXPONENTIAL && p_poly[6].op == AB_OP_SUM);
+  static_assert(!ab::Polynomial<2>::is_defined_for<Vec3, Vec3>(), "Polynomial is defined between doubles");
+  auto p_poly3 = (ab::Polynomial<2>(1.) + se).program<Vec3, Vec3>();
+  EXPECT(p_poly3.size() == 1 && p_poly3[0].op == AB_OP_SQUARED_EXPONENTIAL);
+
   // model parameters and tunable view
   auto model = ab::gp_from_covariance(cov, "check");
   EXPECT(model.get_name() == "check");
@@ -289,6 +304,39 @@ static void scenario_measurement_only() {
   dump("meas.predict.joint", fit_model.predict(test).joint());
   dump("meas.predict_with_noise.marginal", fit_model.predict_with_measurement_noise(test).marginal());
   dump("meas.nll", -(model.log_likelihood(data) - model.prior_log_likelihood()));
+}
+
+static void scenario_polynomial() {
+  // examples/sinc_example.cc:82-89 ("radial"): Polynomial<1> + SE + measurement_only(noise) on a sinc with a
+  // linear trend (the example's truth, sinc_example_utils.hpp)
+  const std::size_t n = 250;
+  std::mt19937 gen(5);
+  std::uniform_real_distribution<double> u(-3., 7.);
+  std::vector<double> xs(n);
+  VectorXd y(static_cast<Index>(n));
+  for (std::size_t i = 0; i < n; ++i) {
+    xs[i] = u(gen);
+    const double z = 0.9 * (xs[i] - 1.);
+    y[static_cast<Index>(i)] = 2. + 0.6 * xs[i] + 5. * (z == 0. ? 1. : std::sin(z) / z);
+  }
+  ab::RegressionDataset<double> data(xs, y);
+  dump("poly.x", data.features);
+  dump("poly.y", data.targets.mean);
+  ab::Polynomial<1> linear(100.);
+  linear.set_param_value("sigma_polynomial_0", 3.0);
+  linear.set_param_value("sigma_polynomial_1", 0.7);
+  auto cov = linear + SE(3.5, 5.7) + ab::measurement_only(ab::IndependentNoise<double>(0.4));
+  auto model = ab::gp_from_covariance(cov);
+  const auto fit_model = model.fit(data);
+  dump("poly.information", fit_model.get_fit().information);
+  std::vector<double> test = {data.features[0], data.features[9], -4., 0., 2.5, 8.};
+  dump("poly.test", test);
+  dump("poly.predict.marginal", fit_model.predict(test).marginal());
+  dump("poly.predict.joint", fit_model.predict(test).joint());
+  dump("poly.predict_with_noise.marginal", fit_model.predict_with_measurement_noise(test).marginal());
+  dump("poly.nll", -(model.log_likelihood(data) - model.prior_log_likelihood()));
+  dump("poly.gram", cov(std::vector<double>(xs.begin(), xs.begin() + 12)));
+  dump("poly.loo.mean", model.cross_validate().predict(data, ab::LeaveOneOutGrouper()).mean());
 }
 
 static void scenario_3d() {
@@ -670,6 +718,7 @@ int main(int argc, char **argv) {
       host_checks();
       scenario_sinc();
       scenario_measurement_only();
+      scenario_polynomial();
       scenario_3d();
       scenario_sparse();
       scenario_sparse_measurement_only();

@@ -18,6 +18,10 @@ Writes tests/golden/ref_outputs_r2.npz (merged into the `golden` fixture by test
               factorisation starts at this size): information, NLL, predictions, LOO — about 3 minutes of
               single-core Eigen LDLT.
 
+  poly        Polynomial<1> + SE + measurement_only(IndependentNoise) — the covariance of the reference's sinc
+              example (examples/sinc_example.cc:84-87), menu entry 11: Gram matrices in both pairings, exact GP
+              and sparse GP on sinc-shaped data with a linear trend.
+
 Sections not named on the command line keep their previous arrays.
 """
 import os
@@ -120,7 +124,34 @@ def section_big(out):
     out["big_loo_mean"], out["big_loo_var"], out["big_loo_score"] = m, v, np.array(s)
 
 
-SECTIONS = {"sparse_mo": section_sparse_mo, "ldlt": section_ldlt, "sparse_nested": section_sparse_nested,
+P11 = [3.0, 0.7, 3.5, 5.7, 0.4]   # sigma_polynomial_0, _1, SE length scale, SE sigma, noise sigma
+
+
+def section_poly(out):
+    x = Ref.random_features(300, 1, 21).ravel() - 3.0      # (-3, 7): both signs, as in the sinc example
+    y = 2.0 + 0.6 * x + 5.0 * np.sinc(0.3 * (x - 1.0)) + 0.4 * Ref.random_normal(300, 22)
+    t = np.concatenate([x[:3], np.linspace(-4.0, 8.0, 9)])
+    out["poly_x"], out["poly_y"], out["poly_test"] = x, y, t
+    out["poly_gram_meas"] = Ref.gram_sym(11, P11, x[:40], as_meas=True)
+    out["poly_gram_plain"] = Ref.gram_sym(11, P11, x[:40], as_meas=False)
+    out["poly_gram_cross"] = Ref.gram_cross(11, P11, x[:40], t)
+    out["poly_information"] = Ref.gp_fit(11, P11, x, y)["information"]
+    out["poly_nll"] = np.array(Ref.gp_nll(11, P11, x, y)[0])
+    mean, _, cov = Ref.gp_predict(11, P11, x, y, t, 2)
+    out["poly_mean"], out["poly_cov"] = mean, cov
+    out["poly_var"] = Ref.gp_predict(11, P11, x, y, t, 1)[1]
+    out["poly_noisy_var"] = Ref.gp_predict(11, P11, x, y, t, 5)[1]
+    m, v, _, s = Ref.gp_cv(11, P11, x, y, 0, 0.0, what=1, want_score=True)
+    out["poly_loo_mean"], out["poly_loo_var"], out["poly_loo_score"] = m, v, np.array(s)
+    u = Ref.uniform_inducing_points(x, 16)
+    out["poly_u"] = u
+    for tag, gk, ga in (("fitc", 0, 0.0), ("pitc", 2, 2.0)):
+        r = Ref.sparse_gp(11, P11, x, y, u, gk, ga, test=t, what=2, want_ll=True)
+        out[f"poly_sp_{tag}_mean"], out[f"poly_sp_{tag}_cov"] = r["mean"], r["cov"]
+        out[f"poly_sp_{tag}_ll"] = np.array(r["ll"])
+
+
+SECTIONS = {"poly": section_poly, "sparse_mo": section_sparse_mo, "ldlt": section_ldlt, "sparse_nested": section_sparse_nested,
             "big": section_big}
 
 

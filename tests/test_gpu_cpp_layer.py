@@ -144,6 +144,28 @@ def test_measurement_only(dumped):
     assert abs(d["meas.nll"][0] - nll) <= RTOL * abs(nll)
 
 
+def test_polynomial_sinc_example(dumped):
+    """examples/sinc_example.cc:82-89: Polynomial<1> + SE + measurement_only(noise) through the trait layer."""
+    d = dumped
+    x, y, t = d["poly.x"], d["poly.y"], d["poly.test"]
+    p = [3.0, 0.7, 3.5, 5.7, 0.4]
+    assert_close(d["poly.gram"].reshape(12, 12).T, Ref.gram_sym(11, p, x[:12]), 1e-13, "gram")
+    assert_close(d["poly.information"], Ref.gp_fit(11, p, x, y)["information"], RTOL, "information")
+    mean, _, cov = Ref.gp_predict(11, p, x, y, t, 2)
+    scale = np.max(np.abs(cov))
+    assert_close(d["poly.predict.marginal.mean"], mean, RTOL)
+    assert np.max(np.abs(d["poly.predict.joint.cov"].reshape(6, 6).T - cov)) <= 1e-9 * scale
+    assert np.max(np.abs(d["poly.predict.marginal.var"] - np.diag(cov))) <= 1e-9 * scale
+    mean, var, _ = Ref.gp_predict(11, p, x, y, t, 5)
+    assert np.max(np.abs(d["poly.predict_with_noise.marginal.var"] - var)) <= 1e-9 * scale
+    nll, _ = Ref.gp_nll(11, p, x, y)
+    assert abs(d["poly.nll"][0] - nll) <= RTOL * abs(nll)
+    m, _, _, _ = Ref.gp_cv(11, p, x, y, 0, 0.0, what=1, want_score=True)
+    assert_close(d["poly.loo.mean"], m, RTOL, "LOO mean")
+    # the linear prior extrapolates the trend: far outside the data the mean keeps rising
+    assert d["poly.predict.marginal.mean"][5] > d["poly.predict.marginal.mean"][2] + 3.0
+
+
 def test_3d_gram_and_gp(dumped):
     d = dumped
     x = d["v3.x"].reshape(-1, 3)

@@ -227,3 +227,42 @@ def test_live_reference_generators_match_numpy_port():
     u = (raw[0::2] + raw[1::2] * 4294967296.0) / 18446744073709551616.0
     want = Ref.random_features(n, 1, seed).ravel()
     assert_close(u * 10.0, want, 1e-15)
+
+
+# ---- Polynomial<order> (polynomials.hpp:63-90): the sinc example's covariance, menu entry 11 ---------------
+
+P11 = [3.0, 0.7, 3.5, 5.7, 0.4]
+
+
+def test_polynomial_fixture(golden):
+    """Polynomial<1> + SE + measurement_only(noise) (examples/sinc_example.cc:84-87) — the restatement against
+    the outputs of the compiled reference: both pairings of the Gram matrix, the exact GP and the sparse GP."""
+    from oracle.oracle import menu_program, menu_program_plain
+    _, ref = golden
+    x, y, t, u = ref["poly_x"], ref["poly_y"], ref["poly_test"], ref["poly_u"]
+    meas, plain = menu_program(11, P11), menu_program_plain(11, P11)
+    assert_close(Restate.gram_sym(*meas, x[:40]), ref["poly_gram_meas"], 1e-13)
+    assert_close(Restate.gram_sym(*plain, x[:40]), ref["poly_gram_plain"], 1e-13)
+    assert_close(Restate.gram_cross(*plain, x[:40], t), ref["poly_gram_cross"], 1e-13)
+    # sigma_0^2 + sigma_1^2 x y on top of the radial part
+    i, j = 3, 17
+    want = P11[0] ** 2 + P11[1] ** 2 * x[i] * x[j] + Restate.cov_eval([SE], P11[2:4], x[i], x[j])
+    assert abs(ref["poly_gram_plain"][i, j] - want) <= 1e-13 * abs(want)
+    assert_close(Restate.gp_fit(*meas, x, y)["information"], ref["poly_information"], 1e-8)
+    nll = Restate.gp_nll(*meas, x, y)
+    assert abs(nll - float(ref["poly_nll"])) <= 1e-10 * abs(float(ref["poly_nll"]))
+    for tag, gk, ga in (("fitc", 0, 0.0), ("pitc", 2, 2.0)):
+        r = Restate.sparse_gp(*meas, x, y, u, group_keys(x, gk, ga), test=t, what=2, want_ll=True,
+                              fu=plain, uu=plain)
+        assert_close(r["mean"], ref[f"poly_sp_{tag}_mean"], 1e-7)
+        want = float(ref[f"poly_sp_{tag}_ll"])
+        assert abs(r["ll"] - want) <= 1e-8 * abs(want)
+
+
+@needs_ref
+def test_live_reference_polynomial():
+    from oracle.oracle import menu_program, menu_program_plain
+    x = features(60, 1, 77).ravel() - 4.0
+    got = Restate.gram_sym(*menu_program(11, P11), x)
+    assert_close(got, Ref.gram_sym(11, P11, x, as_meas=True), 1e-14)
+    assert_close(Restate.gram_sym(*menu_program_plain(11, P11), x), Ref.gram_sym(11, P11, x), 1e-14)
