@@ -1,7 +1,7 @@
 """World-1 run of the distributed factorisation next to the single-GPU one (development aid): isolates what the
 block-column algorithm itself costs (panel width = DMMA k-depth, per-step launches, packing) from communication.
 
-    python tools/dist_w1_bench.py [n]"""
+    python tools/dist_w1_bench.py [n] [ENV=value+ENV=value ...]"""
 import os
 import sys
 
@@ -26,8 +26,9 @@ def main():
     print(f"single-GPU potrf      n={n}: factor {t['factor_ms']:.1f} ms = {fl / t['factor_ms'] * 1e-9:.2f} TFLOP/s, "
           f"solve {t['solve_ms']:.1f} ms", flush=True)
     h.trim()
-    for spec in ("AB_DIST_NB=1024", "AB_DIST_NB=512", "AB_DIST_NB=512+AB_DIST_NBUF=4", "AB_DIST_NB=2048",
-                 "AB_DIST_NB=1024+AB_DIST_SCHEDULE=lookahead1"):
+    specs = sys.argv[2:] or ["AB_DIST_NB=1024", "AB_DIST_NB=512", "AB_DIST_NB=2048",
+                             "AB_DIST_NB=1024+AB_DIST_SCHEDULE=lookahead1"]
+    for spec in specs:
         for kv in spec.split("+"):
             k, v = kv.split("=")
             os.environ[k] = v

@@ -11,7 +11,8 @@ def main():
     h = capi.Handle(0)
     shapes = [(8192, 8192, 8192, False, True, False), (8192, 8192, 8192, False, False, False),
               (8192, 8192, 8192, True, False, False), (16384, 16384, 1024, False, True, False),
-              (16384, 16384, 1024, False, True, True), (16384, 16384, 256, False, True, True),
+              (16384, 16384, 1024, False, True, True), (16384, 16384, 512, False, True, True),
+              (65536, 8192, 512, False, True, False), (16384, 16384, 256, False, True, True),
               (16384, 16384, 64, False, True, True), (4096, 4096, 4096, False, True, True),
               (2048, 2048, 2048, False, True, True), (1024, 1024, 1024, False, True, True),
               (512, 512, 512, False, True, True), (256, 256, 256, False, True, True),
