@@ -25,7 +25,6 @@
 
 #include <cuda.h>
 
-#include <cmath>
 #include <cstdlib>
 
 namespace ab {
@@ -93,7 +92,7 @@ __global__ void __launch_bounds__(TTHREADS, 2)
 gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                    int64_t m, int64_t n, int64_t k, double alpha, double beta, double *C, int64_t ldc,
                    int tiles_m, int tiles_n, int lower, int vec_ok, int cyc_blk, int64_t cyc_stride,
-                   int64_t b_row0, int cinit) {
+                   int64_t b_row0) {
   extern __shared__ __align__(1024) unsigned char tsmem[];
   __shared__ __align__(8) unsigned long long bars[2 * TSTAGES]; // full[0..S), empty[S..2S)
 
@@ -179,36 +178,6 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       acc[nf][mf][0] = 0.;
       acc[nf][mf][1] = 0.;
     }
-  }
-
-  // cinit (|alpha| == |beta| == 1, the trailing updates): the accumulators START at (beta / alpha) C, an
-  // exact sign flip, so the 16 independent 16-byte reads of C are in flight while the first TMA boxes land
-  // and the epilogue only stores.  Reading C in the epilogue instead costs every tile a chain of 16
-  // dependent global round trips (load, fma, store, next load: the stores may alias the next load for all
-  // the compiler knows) — a fixed cost per tile worth ~65 k-iterations, i.e. 11 % at k = 512
-  // (profiles/r02a_gemm_sweep.txt: 34.4 TFLOP/s at k = 1024, 29.2 at k = 256).
-  if (cinit && m0 + TBM <= m && n0 + TBN <= n) { // interior tiles; edge tiles read C in the epilogue
-    const double *src = C + (m0 + wm * (TBM / TWARPS_M) + 2 * lr) + (n0 + wn * (TBN / TWARPS_N) + lq) * ldc;
-#pragma unroll
-    for (int nf = 0; nf < TNF; ++nf) {
-#pragma unroll
-      for (int mf = 0; mf < TMF; ++mf) {
-        const double2 c = *reinterpret_cast<const double2 *>(src + mf * 8 + nf * 8 * ldc);
-        acc[nf][mf][0] = c.x;
-        acc[nf][mf][1] = c.y;
-      }
-    }
-    if (beta != alpha) { // beta / alpha == -1
-#pragma unroll
-      for (int nf = 0; nf < TNF; ++nf) {
-#pragma unroll
-        for (int mf = 0; mf < TMF; ++mf) {
-          acc[nf][mf][0] = -acc[nf][mf][0];
-          acc[nf][mf][1] = -acc[nf][mf][1];
-        }
-      }
-    }
-    beta = 0.; // C is inside the accumulators now
   }
 
   for (int kt = 0; kt < ktiles; ++kt) {
@@ -371,15 +340,9 @@ int gemm_nt_tma(ab_handle_s *h, bool lower, int64_t m, int64_t n, int64_t k, dou
   const int64_t tn = (n + TBN - 1) / TBN;
   AB_REQUIRE(tm * tn < (int64_t(1) << 31), "GEMM grid too large");
   const int vec_ok = aligned16(C) ? 1 : 0;
-  // AB_GEMM_CINIT=0 (read once; an A/B switch for the benches): read C in the epilogue as the cp.async kernel does
-  static const bool cinit_on = []() {
-    const char *e = std::getenv("AB_GEMM_CINIT");
-    return e == nullptr || e[0] != '0';
-  }();
-  const int cinit = cinit_on && vec_ok && std::fabs(alpha) == 1. && std::fabs(beta) == 1. ? 1 : 0;
   gemm_nt_tma_kernel<<<static_cast<unsigned>(tm * tn), TTHREADS, smem, h->stream>>>(
       mapA, mapB, m, n, k, alpha, beta, C.p, C.ld, static_cast<int>(tm), static_cast<int>(tn), lower ? 1 : 0, vec_ok,
-      cyclic ? static_cast<int>(cyc->blk) : 0, cyclic ? cyc->stride : 0, cyclic ? cyc->row0 : 0, cinit);
+      cyclic ? static_cast<int>(cyc->blk) : 0, cyclic ? cyc->stride : 0, cyclic ? cyc->row0 : 0);
   AB_LAUNCHED(h);
   return AB_OK;
 }

@@ -58,10 +58,10 @@ def test_unsupported_forms_fail_loudly(handle):
     x = np.linspace(0.0, 1.0, 10)
     with pytest.raises(capi.AbError) as e:   # inside a product: no device form, no fallback
         handle.gram_sym([POLY, SE, PROD], [1.0, 1.0, 1.0, 1.0, 0, 0], x)
-    assert e.value.status == 3
+    assert "UNSUPPORTED" in str(e.value)
     with pytest.raises(capi.AbError) as e:   # Polynomial is defined between doubles only (polynomials.hpp:79)
         handle.gram_sym(*PLAIN, np.zeros((10, 3)))
-    assert e.value.status == 3
+    assert "UNSUPPORTED" in str(e.value)
     with pytest.raises(capi.AbError):        # non-integer degree
         handle.gram_sym([POLY], [1.0, 1.5], x)
 
