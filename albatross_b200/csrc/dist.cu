@@ -219,6 +219,7 @@ struct StreamSwap {
 struct DistEvents {
   std::vector<cudaEvent_t> wait_begin, wait_end, panel_begin, panel_end;
   std::vector<cudaEvent_t> arrived, bulkdone, pdone; // per panel: broadcast landed / S done with it / PS done
+  std::vector<cudaEvent_t> coldone; // per panel: S's single-column update with it is done (paired schedule)
   std::vector<char> owned; // panel k was factored by this rank in the most recent fit
   cudaEvent_t factor_end = nullptr;
   int64_t steps = 0;
@@ -247,13 +248,14 @@ DistEvents &dist_events(ab_handle_s *h, int64_t nblk) {
     ev.wait_end.push_back(e[1]);
     ev.panel_begin.push_back(e[2]);
     ev.panel_end.push_back(e[3]);
-    cudaEvent_t q[3];
+    cudaEvent_t q[4];
     for (auto &x : q) {
       cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
     }
     ev.arrived.push_back(q[0]);
     ev.bulkdone.push_back(q[1]);
     ev.pdone.push_back(q[2]);
+    ev.coldone.push_back(q[3]);
   }
   ev.steps = nblk;
   ev.owned.assign(static_cast<size_t>(nblk), 0);
@@ -328,14 +330,37 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   // (3099 vs 3126 with 2 at N = 131 072 on 8 GPUs; 8 buffers: 3345 — a chain far ahead of the updates competes
   // with them for HBM); profiles/r02i_*, r02j_*, r02k_*
   int64_t NBUF = pipelined ? (W <= 2 ? 2 : 4) : 2;
+  // Paired updates (default in the pipelined schedule; AB_DIST_PAIR=0 for the one-panel-per-launch form):
+  // the update stream applies panels 2q and 2q+1 in ONE launch of k-depth 2 nb.  The DMMA kernel pays a
+  // fixed cost per output tile (pipeline fill, read-modify-write of C), so a trailing update of depth 512
+  // runs 3-4 % below one of depth 1024 (world-1 runs of this routine at N = 65 536: 32.3 vs 33.5 TFLOP/s,
+  // profiles/r02p_dist_w1.txt) while the panel CHAIN wants narrow panels (it is sequential across the ranks).
+  // Pairing keeps the chain at nb and gives the bulk update 2 nb.  The two panels of a pair lie side by side
+  // in one buffer with a common leading dimension and row origin (block row 2q), so that [P_2q | P_2q+1] is
+  // one operand; panel 2q+1 leaves its first nb rows unused.
+  bool pairing = pipelined;
+  if (const char *e = std::getenv("AB_DIST_PAIR")) {
+    pairing = pairing && e[0] != '0';
+  }
+  if (const char *e = std::getenv("AB_DIST_PCOL")) {
+    pairing = pairing && e[0] != '0';
+  }
+  if (pairing) {
+    NBUF = W <= 2 ? 4 : 6; // in panels: 2 / 3 pair buffers
+  }
   if (const char *e = std::getenv("AB_DIST_NBUF")) {
     NBUF = std::max<int64_t>(2, std::min<int64_t>(16, std::atoll(e)));
   }
   if (!pipelined) {
     NBUF = 2;
   }
-  std::vector<void *> pb(static_cast<size_t>(NBUF), nullptr);
-  const size_t pbytes = static_cast<size_t>(ldp_max) * static_cast<size_t>(nb) * sizeof(double);
+  if (pairing) {
+    NBUF = std::max<int64_t>(4, NBUF + (NBUF & 1)); // whole pair buffers, at least two of them
+  }
+  const int64_t nslots = pairing ? NBUF / 2 : NBUF;
+  std::vector<void *> pb(static_cast<size_t>(nslots), nullptr);
+  const size_t pbytes =
+      static_cast<size_t>(ldp_max) * static_cast<size_t>(nb) * sizeof(double) * (pairing ? 2 : 1);
   for (auto &b : pb) {
     AB_TRY(sc.alloc(pbytes, &b));
   }
@@ -348,8 +373,19 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   }
   // accounting (ab_dist_fit_breakdown): time S spends waiting for a panel, time of the panel chains
   DistEvents &ev = dist_events(h, nblk);
+  // the packed panel k as a view whose row 0 is global row origin(k): k * nb, or the pair's first row
+  auto origin = [&](int64_t k) { return (pairing ? (k & ~int64_t(1)) : k) * nb; };
   auto panel = [&](int64_t k) {
-    return MatView{static_cast<double *>(pb[static_cast<size_t>(k % NBUF)]), round_up(n - k * nb, 2)};
+    const int64_t ld = round_up(n - origin(k), 2);
+    if (!pairing) {
+      return MatView{static_cast<double *>(pb[static_cast<size_t>(k % NBUF)]), ld};
+    }
+    return MatView{static_cast<double *>(pb[static_cast<size_t>((k / 2) % nslots)]) + (k & 1) * nb * ld, ld};
+  };
+  // panels k and k+1 (k even) go to the bulk update as one operand of depth 2 nb
+  auto paired = [&](int64_t k) {
+    const int64_t head = k & ~int64_t(1);
+    return pairing && head + 1 < nblk && width(head + 1) == nb;
   };
   // owner only, on PS: factor block column k (diagonal potrf + TRSM of the rows below) and pack it
   auto factor_and_pack = [&](int64_t k) -> int {
@@ -361,7 +397,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     AB_TRY(potrf(h, D, wk, dinv_of(k), static_cast<int *>(d_bad) + k,
                  static_cast<double *>(d_floor) + (k / W) * nb));
     AB_TRY(trsm_right_lower_T(h, D, dinv_of(k), wk, D.sub(wk, 0), hk - wk));
-    const MatView Pk = panel(k);
+    const MatView Pk = panel(k).sub(r0 - origin(k), 0);
     AB_CUDA(cudaMemcpy2DAsync(Pk.p, Pk.ld * sizeof(double), D.p, D.ld * sizeof(double),
                               static_cast<size_t>(hk) * sizeof(double), static_cast<size_t>(wk),
                               cudaMemcpyDeviceToDevice, PS));
@@ -372,7 +408,7 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   // One column at a time (the look-ahead column, and the fallback for shapes the TMA kernel does not take):
   auto update = [&](int64_t j, int64_t k) -> int {
     const MatView Pk = panel(k);
-    const int64_t off = (j - k) * nb;
+    const int64_t off = j * nb - origin(k);
     return gemm(h, GEMM_TRANS_B, n - j * nb, width(j), width(k), -1., Pk.sub(off, 0), Pk.sub(off, 0), 1.,
                 colblk(j).sub(j * nb, 0));
   };
@@ -382,7 +418,8 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
   // wave each (measured at N = 65 536 on 2 GPUs: 0.87 of the 1-GPU rate, 214 ms of tails in 1.6 s; the
   // launches of one step carry 1/W of a full trailing update, so the loss grows with W).
   // count = -1: every owned column from jfirst on; count = 1: block column jfirst alone.
-  auto update_cols = [&](int64_t jfirst, int64_t count, int64_t k) -> int {
+  // npanels = 2: panels k and k+1 of a pair (k even) in one launch of depth 2 nb.
+  auto update_cols = [&](int64_t jfirst, int64_t count, int64_t k, int64_t npanels = 1) -> int {
     if (jfirst >= nblk) {
       return AB_OK;
     }
@@ -394,17 +431,20 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     CyclicB cyc;
     cyc.blk = nb;
     cyc.stride = static_cast<int64_t>(W) * nb;
-    cyc.row0 = (jfirst - k) * nb;
-    cyc.rows = n - k * nb;
+    cyc.row0 = R0 - origin(k);
+    cyc.rows = n - origin(k);
     int st = AB_ERR_UNSUPPORTED;
-    if (gemm_tma_enabled() && width(k) == nb) {
-      st = gemm_nt_tma(h, true, m, ncols, nb, -1., Pk.sub(R0 - k * nb, 0), Pk, 1., A.sub(R0, l0 * nb), &cyc);
+    if (gemm_tma_enabled() && width(k + npanels - 1) == nb) {
+      st = gemm_nt_tma(h, true, m, ncols, npanels * nb, -1., Pk.sub(R0 - origin(k), 0), Pk, 1.,
+                       A.sub(R0, l0 * nb), &cyc);
     }
     if (st != AB_ERR_UNSUPPORTED) {
       return st;
     }
-    for (int64_t j = jfirst; j <= jlast; j += W) {
-      AB_TRY(update(j, k));
+    for (int64_t kk = k; kk < k + npanels; ++kk) {
+      for (int64_t j = jfirst; j <= jlast; j += W) {
+        AB_TRY(update(j, kk));
+      }
     }
     return AB_OK;
   };
@@ -453,8 +493,10 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
         AB_CUDA(cudaStreamWaitEvent(CS, pdone[prev], 0));
       }
       if (W > 1) {
-        AB_NCCL(g_nccl.Broadcast(Pk.p, Pk.p, static_cast<size_t>(Pk.ld * width(k)), ncclDouble, root,
-                                 comm_of(h), CS));
+        // from the panel's own first row (k * nb) to the end of its last column
+        double *first = Pk.p + (k * nb - origin(k));
+        const size_t count = static_cast<size_t>((width(k) - 1) * Pk.ld + (n - k * nb));
+        AB_NCCL(g_nccl.Broadcast(first, first, count, ncclDouble, root, comm_of(h), CS));
       }
       AB_CUDA(cudaEventRecord(arrived[k], CS));
       return AB_OK;
@@ -491,7 +533,9 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
         // with them before PS takes the column over
         const int64_t handover = pcol_always ? jstar - W - 1 : k - 1;
         if ((!pcol_always || k == std::max<int64_t>(jstar - W, 0)) && handover >= 0) {
-          AB_CUDA(cudaStreamWaitEvent(PS, bulkdone[handover], 0));
+          // paired schedule: the head of a pair reaches this column in a launch of its own (below)
+          const bool head = paired(handover) && (handover & 1) == 0;
+          AB_CUDA(cudaStreamWaitEvent(PS, head ? ev.coldone[handover] : bulkdone[handover], 0));
         }
         {
           StreamSwap swap(h, PS);
@@ -506,8 +550,22 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
       AB_CUDA(cudaEventRecord(ev.wait_begin[k], S));
       AB_CUDA(cudaStreamWaitEvent(S, arrived[k], 0));
       AB_CUDA(cudaEventRecord(ev.wait_end[k], S));
-      AB_TRY(update_cols(p_takes ? jstar + W : jstar, -1, k));
-      AB_CUDA(cudaEventRecord(bulkdone[k], S));
+      if (!paired(k)) {
+        AB_TRY(update_cols(p_takes ? jstar + W : jstar, -1, k));
+        AB_CUDA(cudaEventRecord(bulkdone[k], S));
+      } else if ((k & 1) == 0) {
+        // head of a pair: wait for its partner — except for the one column that PS takes over with the
+        // partner already (I own k + 1, so PS applies panels k + 1 .. to my NEXT column k + 1 + W)
+        if (jstar == k + 1) {
+          AB_TRY(update_cols(jstar + W, 1, k));
+        }
+        AB_CUDA(cudaEventRecord(ev.coldone[k], S));
+      } else {
+        // tail: panels k - 1 and k to every owned column beyond the one PS holds, depth 2 nb
+        AB_TRY(update_cols(jstar + W, -1, k - 1, 2));
+        AB_CUDA(cudaEventRecord(bulkdone[k - 1], S));
+        AB_CUDA(cudaEventRecord(bulkdone[k], S));
+      }
       // ---- CS: the next panel
       if (k + 1 < nblk) {
         AB_TRY(bcast_p(k + 1));

@@ -137,11 +137,17 @@ def test_world1_broadcast_and_breakdown(handle):
     df.free()
 
 
-@pytest.mark.parametrize("schedule", ["lookahead1", "pipeline"])
+@pytest.mark.parametrize("schedule", ["lookahead1", "pipeline", "pipeline_unpaired", "pipeline_nbuf8"])
 def test_dist_schedules_agree(handle, schedule, monkeypatch):
-    """Both schedules of the distributed factorisation (AB_DIST_SCHEDULE) give the oracle's answer."""
+    """Every schedule of the distributed factorisation (AB_DIST_SCHEDULE, AB_DIST_PAIR, AB_DIST_NBUF) gives the
+    oracle's answer: round-1 style look-ahead, the panel pipeline with paired (default) and single-panel bulk
+    updates, and a deeper ring of packed-panel buffers."""
     if schedule == "lookahead1":
         monkeypatch.setenv("AB_DIST_SCHEDULE", "lookahead1")
+    elif schedule == "pipeline_unpaired":
+        monkeypatch.setenv("AB_DIST_PAIR", "0")
+    elif schedule == "pipeline_nbuf8":
+        monkeypatch.setenv("AB_DIST_NBUF", "8")
     ops, pp = prog(6)
     x = features(1700, 1, 9).ravel()
     y = targets(x)
