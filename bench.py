@@ -702,7 +702,7 @@ def run_device_dist(args):
                                    "leg): one matrix, block-column-cyclic over the ranks, NCCL "
                                    "panel broadcasts; two Gram builds + two factorisations per step",
                        "flops_per_step": "2*N^3/3", "parallelism": f"block-cyclic 1x{world}, "
-                                                                   f"nb={nb_eff}, decoupled panel pipeline",
+                                                                   f"nb={nb_eff}, decoupled panel pipeline, bulk updates in panel pairs (depth {2 * nb_eff})",
                        "l2_policy": "inputs (matrix shard >= 17 GB) larger than L2",
                        "scaling_note": "total work fixed for N_gpus = 2/4/8; the 1-GPU line is "
                                        "N=65536 (the same metric, FLOP/s, on 1/8 of the flops)"},
