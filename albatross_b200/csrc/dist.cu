@@ -53,6 +53,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr; // optional
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr; // optional
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
@@ -95,6 +96,7 @@ int load_nccl() {
 #undef AB_NCCL_SYM
   g_nccl.CommInitRankConfig =
       reinterpret_cast<decltype(g_nccl.CommInitRankConfig)>(dlsym(lib, "ncclCommInitRankConfig"));
+  g_nccl.CommSplit = reinterpret_cast<decltype(g_nccl.CommSplit)>(dlsym(lib, "ncclCommSplit"));
   g_nccl.lib = lib;
   return AB_OK;
 }
@@ -109,6 +111,17 @@ int load_nccl() {
   } while (0)
 
 ncclComm_t comm_of(const ab_handle_s *h) { return static_cast<ncclComm_t>(h->comm); }
+
+// Second communicator of the same ranks WITHOUT the CTA cap (ab_dist_init): used for the panel broadcasts of
+// the chain-bound tail of the factorisation, where the broadcast is on the critical path and the update stream
+// has SMs to spare.  Keyed by handle; absent when NCCL has no ncclCommSplit or the cap is off.
+std::map<const ab_handle_s *, ncclComm_t> g_tail_comm;
+std::mutex g_tail_comm_mu;
+ncclComm_t tail_comm_of(const ab_handle_s *h) {
+  std::lock_guard<std::mutex> lock(g_tail_comm_mu);
+  auto it = g_tail_comm.find(h);
+  return it == g_tail_comm.end() ? nullptr : it->second;
+}
 
 // out[i] = a[i] - b[i]
 __global__ void sub_kernel(const double *a, const double *b, int64_t n, double *out) {
@@ -480,6 +493,30 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
     // lag up to NBUF - 1 panels behind (NBUF packed-panel buffers), which also lets ranks whose share of a
     // step is one block column larger (4 % of the work at W = 8) drift instead of stalling the others.
     std::vector<cudaEvent_t> &arrived = ev.arrived, &bulkdone = ev.bulkdone, &pdone = ev.pdone;
+    // Chain-bound tail: with r rows left a rank's share of the bulk update takes r^2 nb / (W R) (R = 33 TFLOP/s)
+    // and one chain step ~0.6 ms + r * 5.9e-8 s (column update 2 nb^2 / 31 TFLOP/s + TRSM nb^2 / 12 TFLOP/s +
+    // broadcast 8 nb / 200 GB/s per row at nb = 512, potrf 0.56 ms; tools/chain_bench.py,
+    // profiles/r02w_chain_bench.txt).  From the step where the chain is the longer of the two, the broadcasts go
+    // through the uncapped communicator (AB_DIST_TAIL_COMM=0: never).  N = 131 072 on 8 GPUs: 3003 -> 2985 ms
+    // (profiles/r02z_*).  Measured and dropped in the same run: factoring the diagonal block while a second
+    // panel stream updates the rows below it (no change: 3002.9 vs 3003.4 ms).
+    ncclComm_t tail_comm = W > 1 ? tail_comm_of(h) : nullptr;
+    if (const char *e = std::getenv("AB_DIST_TAIL_COMM")) {
+      if (e[0] == '0') {
+        tail_comm = nullptr;
+      }
+    }
+    int64_t tail_from = nblk;
+    for (int64_t k = 0; k < nblk; ++k) {
+      const double r = static_cast<double>(n - k * nb);
+      const double bulk = r * r * static_cast<double>(nb) / (W * 33e12);
+      const double chain = 0.6e-3 + r * 5.9e-8 * (static_cast<double>(nb) / 512.);
+      if (bulk < chain) {
+        tail_from = k;
+        break;
+      }
+    }
+
     auto first_owned_after = [&](int64_t k) { return k + 1 + ((me - (k + 1)) % W + W) % W; };
     // C stream: broadcast of panel k into buffer k % NBUF
     auto bcast_p = [&](int64_t k) -> int {
@@ -496,7 +533,8 @@ int dist_fit_impl(ab_handle_s *h, const DevProg &P, const ab_matrix_s *F, const 
         // from the panel's own first row (k * nb) to the end of its last column
         double *first = Pk.p + (k * nb - origin(k));
         const size_t count = static_cast<size_t>((width(k) - 1) * Pk.ld + (n - k * nb));
-        AB_NCCL(g_nccl.Broadcast(first, first, count, ncclDouble, root, comm_of(h), CS));
+        AB_NCCL(g_nccl.Broadcast(first, first, count, ncclDouble, root,
+                                 k >= tail_from && tail_comm != nullptr ? tail_comm : comm_of(h), CS));
       }
       AB_CUDA(cudaEventRecord(arrived[k], CS));
       return AB_OK;
@@ -774,6 +812,14 @@ int ab_dist_init(ab_handle h, int rank, int world, const void *id) {
     AB_NCCL(g_nccl.CommInitRank(&comm, world, uid, rank));
   }
   h->comm = comm;
+  if (g_nccl.CommSplit != nullptr && g_nccl.CommInitRankConfig != nullptr && max_ctas > 0) {
+    ncclConfig_t config = NCCL_CONFIG_INITIALIZER;
+    config.maxCTAs = 32;
+    ncclComm_t tail = nullptr;
+    AB_NCCL(g_nccl.CommSplit(comm, 0, rank, &tail, &config));
+    std::lock_guard<std::mutex> lock2(g_tail_comm_mu);
+    g_tail_comm[h] = tail;
+  }
   return ensure_dist_streams(h);
 }
 
@@ -784,6 +830,11 @@ int ab_dist_finalize(ab_handle h) {
     cudaStreamSynchronize(h->stream);
     if (h->comm_stream != nullptr) {
       cudaStreamSynchronize(h->comm_stream);
+    }
+    if (ncclComm_t tail = tail_comm_of(h)) {
+      g_nccl.CommDestroy(tail);
+      std::lock_guard<std::mutex> lock2(g_tail_comm_mu);
+      g_tail_comm.erase(h);
     }
     g_nccl.CommDestroy(comm_of(h));
     h->comm = nullptr;
