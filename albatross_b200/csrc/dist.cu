@@ -1043,9 +1043,12 @@ int ab_dist_factor_broadcast(ab_handle h, ab_factor *factor, int root) {
   phase_begin(h, PH_H2D);
   int status = AB_OK;
   if (n > 0) {
+    // nothing else runs during this transfer: the uncapped communicator when there is one (the 8-CTA cap of
+    // the main one costs 8.6 GB of L 69 ms instead of 19 ms on 8 GPUs, profiles/r02t_bench_8gpu_n131072.json)
+    ncclComm_t wide = tail_comm_of(h) != nullptr ? tail_comm_of(h) : comm_of(h);
     if (g_nccl.Broadcast(f->m->d, f->m->d, static_cast<size_t>(f->m->ld) * static_cast<size_t>(n),
-                         ncclDouble, root, comm_of(h), h->stream) != ncclSuccess ||
-        g_nccl.Broadcast(f->dinv, f->dinv, f->dinv_bytes / sizeof(double), ncclDouble, root, comm_of(h),
+                         ncclDouble, root, wide, h->stream) != ncclSuccess ||
+        g_nccl.Broadcast(f->dinv, f->dinv, f->dinv_bytes / sizeof(double), ncclDouble, root, wide,
                          h->stream) != ncclSuccess) {
       set_error("ncclBroadcast of the factor failed");
       status = AB_ERR_NCCL;
