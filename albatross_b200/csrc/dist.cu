@@ -6,17 +6,20 @@
 //
 //   * ab_dist_gp_fit   - K is generated directly in block-column-cyclic layout (block column j on
 //                        rank j % world, every rank holds all features: no Gram collective), then a
-//                        right-looking blocked Cholesky: the owner factors panel k (potrf of the
-//                        diagonal block + TRSM of the rows below), packs it and broadcasts it
-//                        (ncclBroadcast on a high-priority stream); every rank updates its own block
-//                        columns with DSYRK/DGEMM on the FP64 tensor pipe.  Look-ahead 1: the owner
-//                        of panel k+1 updates and factors it first, so that its broadcast overlaps
-//                        the rest of update k.  On NVSwitch every GPU reaches every peer at full
-//                        bandwidth, so the 1 x P process grid (a block-cyclic layout with P_r = 1)
-//                        moves N^2/2 * 8 bytes per GPU in total — 69 GB at N = 131 072, ~0.2 s at
+//                        right-looking blocked Cholesky over three streams per rank: the panel
+//                        pipeline (high priority) applies every arriving panel to the next block
+//                        column the rank owns and factors it the moment it is complete (potrf of
+//                        the diagonal block + TRSM of the rows below, packed); the broadcasts
+//                        (ncclBroadcast) run on their own stream into a ring of packed-panel
+//                        buffers; the update stream applies panels in PAIRS to all the other block
+//                        columns of the rank in one DSYRK/DGEMM launch of depth 2 nb on the FP64
+//                        tensor pipe.  On NVSwitch every GPU reaches every peer at full bandwidth,
+//                        so the 1 x P process grid (a block-cyclic layout with P_r = 1) moves
+//                        N^2/2 * 8 bytes per GPU in total — 69 GB at N = 131 072, ~0.2 s at
 //                        measured broadcast rates against >3 s of DMMA work — and keeps every
-//                        trailing update a single tall GEMM per block column; a P_r > 1 grid would
-//                        only pay off across nodes.
+//                        trailing update a single tall GEMM; a P_r > 1 grid would only pay off
+//                        across nodes.  AB_DIST_SCHEDULE=lookahead1 keeps the round-1 schedule
+//                        (two buffers, the next owner prepares its panel inside the step).
 //   * forward / backward block substitution for information = K^-1 y, one small reduce / broadcast
 //     per block column; log|K| and y^T K^-1 y by all-reduce of two doubles.
 //   * ab_dist_gram_rows - row-block sharded Gram build.
