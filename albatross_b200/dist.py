@@ -124,3 +124,61 @@ def max_over_ranks(value: float) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def panel_schedule(nblk: int, world: int, rank: int, last_full: bool = True, pairing: bool = True):
+    """Host-side model of the update schedule of the distributed factorisation: which stream applies
+    which packed panel to which block column of this rank, in enqueue order, and which event each
+    operation waits for / records.  Mirrors the pipelined loop of dist_fit_impl
+    (albatross_b200/csrc/dist.cu): the panel stream PS applies every panel k to the first column the
+    rank owns after k and factors a column once panel (column - 1) is in; the update stream S applies
+    the panels to the columns beyond that one — one panel per launch, or, with `pairing`, panels
+    2q and 2q + 1 in one launch of depth 2 nb at the odd step, plus one single-column launch at the
+    even step for the column PS takes over in between.  `last_full`: the last block column has the
+    full width (a ragged last panel is never paired).
+
+    Returns a list of dicts {stream, iter, panels, cols, waits, records} (and {stream: 'PS',
+    iter, factor: j} entries); tests/test_dist_host.py checks the integer contract on it: every
+    (column, earlier panel) pair exactly once, take-over of a column only behind S's last update of it,
+    buffers reused only behind their readers."""
+    W, me = world, rank
+    owned = list(range(me, nblk, W))
+
+    def full(k):
+        return k < nblk - 1 or last_full
+
+    def paired(k):
+        head = k & ~1
+        return pairing and head + 1 < nblk and full(head + 1)
+
+    def first_owned_after(k):
+        return k + 1 + ((me - (k + 1)) % W + W) % W
+
+    def cols_from(j0):
+        return [j for j in owned if j >= j0]
+
+    ops = []
+    for k in range(nblk):
+        jstar = first_owned_after(k)
+        p_takes = jstar < nblk
+        if p_takes:
+            waits = [f"arrived[{k}]"]
+            handover = jstar - W - 1
+            if k == max(jstar - W, 0) and handover >= 0:
+                head = paired(handover) and handover % 2 == 0
+                waits.append(f"{'coldone' if head else 'bulkdone'}[{handover}]")
+            ops.append(dict(stream="PS", iter=k, panels=(k,), cols=[jstar], waits=waits, records=[]))
+        ops.append(dict(stream="PS", iter=k, panels=(), cols=[], waits=[], records=[f"pdone[{k}]"]))
+        if jstar == k + 1 and jstar < nblk:
+            ops.append(dict(stream="PS", iter=k, factor=jstar))
+        if not paired(k):
+            ops.append(dict(stream="S", iter=k, panels=(k,), cols=cols_from(jstar + W if p_takes else jstar),
+                            waits=[f"arrived[{k}]"], records=[f"bulkdone[{k}]"]))
+        elif k % 2 == 0:
+            cols = [jstar + W] if jstar == k + 1 and jstar + W < nblk else []
+            ops.append(dict(stream="S", iter=k, panels=(k,), cols=cols, waits=[f"arrived[{k}]"],
+                            records=[f"coldone[{k}]"]))
+        else:
+            ops.append(dict(stream="S", iter=k, panels=(k - 1, k), cols=cols_from(jstar + W),
+                            waits=[f"arrived[{k}]"], records=[f"bulkdone[{k - 1}]", f"bulkdone[{k}]"]))
+    return ops

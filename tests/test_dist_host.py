@@ -121,3 +121,60 @@ def test_loo_chunks_cover():
     assert got[0][0] == 0 and sum(c[1] for c in got) == n
     for (a, la), (b, _) in zip(got, got[1:]):
         assert a + la == b
+
+
+# ---- the update schedule of the distributed factorisation (dist.cu, pipelined loop) -------------------------
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("nblk", [1, 2, 3, 5, 8, 9, 16, 33])
+@pytest.mark.parametrize("pairing,last_full", [(True, True), (True, False), (False, True)])
+def test_panel_schedule_contract(world, nblk, pairing, last_full):
+    """Integer contract of the panel pipeline, on the host-side model of the loop in dist.cu:
+    (1) every owned block column receives every earlier panel exactly once;
+    (2) the panel stream takes a column over only behind the update stream's last launch on it — the event it
+        waits for is the one that launch records, and it is recorded earlier in enqueue order;
+    (3) on the panel stream a column's panels arrive in increasing order and its factorisation follows the last;
+    (4) no launch uses a panel before the step in which it arrives;
+    (5) with at least four packed-panel buffers (two pair buffers) a buffer is overwritten only after the
+        update-stream launch that read its previous panel has been enqueued."""
+    for rank in range(world):
+        ops = abd.panel_schedule(nblk, world, rank, last_full=last_full, pairing=pairing)
+        owned = list(range(rank, nblk, world))
+        seen = {}
+        first_ps, last_s, factor_pos, recorded_at = {}, {}, {}, {}
+        for pos, op in enumerate(ops):
+            for e in op.get("records", []):
+                recorded_at[e] = (pos, op["iter"])
+            if "factor" in op:
+                factor_pos[op["factor"]] = pos
+                continue
+            for j in op["cols"]:
+                assert j in owned and j < nblk
+                for k in op["panels"]:
+                    assert k < j, (j, k)
+                    assert op["iter"] >= k                                    # (4)
+                    seen[(j, k)] = seen.get((j, k), 0) + 1
+                if op["stream"] == "PS":
+                    first_ps.setdefault(j, pos)
+                else:
+                    last_s[j] = pos
+        assert seen == {(j, k): 1 for j in owned for k in range(j)}, (world, nblk, rank)   # (1)
+        for j in owned:
+            ps_ops = [(pos, op) for pos, op in enumerate(ops)
+                      if op["stream"] == "PS" and j in op.get("cols", [])]
+            ks = [op["panels"][0] for _, op in ps_ops]
+            assert ks == sorted(ks) and (not ks or ks[-1] == j - 1)            # (3)
+            if j > 0:
+                assert factor_pos[j] > ps_ops[-1][0]
+            if j in last_s:                                                    # (2)
+                pos0, op0 = ps_ops[0]
+                assert last_s[j] < pos0
+                gate = [w for w in op0["waits"] if not w.startswith("arrived")]
+                assert len(gate) == 1 and gate[0] in ops[last_s[j]]["records"], (j, gate, ops[last_s[j]])
+                assert recorded_at[gate[0]][0] < pos0
+        nbuf = 4
+        for k in range(nbuf, nblk):                                            # (5)
+            prev = k - nbuf
+            # factor_and_pack_p(k) is enqueued in the panel-stream part of step k - 1, ahead of that step's S part
+            assert recorded_at[f"bulkdone[{prev}]"][1] <= k - 2
+            assert recorded_at[f"pdone[{prev}]"][1] <= k - 2
