@@ -421,11 +421,12 @@ def run_device(args):
                 "peak_source": f"cuBLAS DGEMM {probe_n}^3 via torch.matmul, measured live in this run "
                                "(MEASURED_PEAKS.json carries no fp64 figure)",
                 "launch_ms": kernel_ms,
-                "traffic": 4.7464e10,
+                "traffic": 1.2336e10,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full "
-                                  "of this build (profiles/r02b_ncu_summary.md): 46.92 GB + 0.54 GB = 18 % of "
-                                  "DRAM peak; algorithmic minimum 3 * 8 * 8192^2 = 1.6 GB (tile re-reads served "
-                                  "by HBM instead of L2: tensor-bound, not memory-bound)",
+                                  "of this build (profiles/r02p_ncu_gemm_tma_grouped.md): 11.80 GB + 0.54 GB = "
+                                  "6 % of DRAM peak (46.92 + 0.54 GB before the grouped tile order, "
+                                  "profiles/r02b_ncu_summary.md); algorithmic minimum 3 * 8 * 8192^2 = 1.6 GB "
+                                  "(tile re-reads beyond the 126 MB L2: tensor-bound, not memory-bound)",
                 "phase": {"what": "whole factorisation phase of the step (2 x N^3/3 flops / CUDA-event time, "
                                   "panel kernels and TRSMs included)",
                           "achieved": achieved_phase, "frac": achieved_phase / fp64_peak}}
