@@ -520,6 +520,18 @@ inline MeasurementOnly<SubCovariance> measurement_only(const SubCovariance &cov)
   return MeasurementOnly<SubCovariance>(cov);
 }
 
+// contains_polynomial<K>: K holds a Polynomial<order> somewhere in its tree.  The device adds polynomial terms in a
+// pass over the finished matrix, which works for summands only: a product with one is rejected at compile time.
+template <typename K> struct contains_polynomial : std::false_type {};
+template <int order> struct contains_polynomial<Polynomial<order>> : std::true_type {};
+template <typename Sub> struct contains_polynomial<MeasurementOnly<Sub>> : contains_polynomial<Sub> {};
+template <class LHS, class RHS>
+struct contains_polynomial<SumOfCovarianceFunctions<LHS, RHS>>
+    : std::integral_constant<bool, contains_polynomial<LHS>::value || contains_polynomial<RHS>::value> {};
+template <class LHS, class RHS>
+struct contains_polynomial<ProductOfCovarianceFunctions<LHS, RHS>>
+    : std::integral_constant<bool, contains_polynomial<LHS>::value || contains_polynomial<RHS>::value> {};
+
 // Shared by Sum and Product: parameter plumbing and the one-sided fallbacks of
 // covariance_function.hpp:266-294 / :357-388 (when only one operand is defined for (X, Y) the
 // result is that operand alone).
@@ -586,6 +598,9 @@ public:
 template <class LHS, class RHS>
 class ProductOfCovarianceFunctions
     : public BinaryCovariance<ProductOfCovarianceFunctions<LHS, RHS>, LHS, RHS, AB_OP_PRODUCT> {
+  static_assert(!contains_polynomial<LHS>::value && !contains_polynomial<RHS>::value,
+                "albatross_b200: a Polynomial inside a product has no device form (no CPU fallback)");
+
 public:
   using BinaryCovariance<ProductOfCovarianceFunctions<LHS, RHS>, LHS, RHS, AB_OP_PRODUCT>::BinaryCovariance;
   std::string name() const { return "(" + this->lhs_.get_name() + "*" + this->rhs_.get_name() + ")"; }

@@ -54,6 +54,11 @@ def test_supported_program_compiles(tmp_path):
           ab::RegressionDataset<double> d({1., 2.}, ab::VectorXd({1., 2.}));
           auto fit = model.fit(d);
           (void)fit.predict(std::vector<double>{1.5}).marginal();
+          // the sinc example's covariance: a Polynomial as a summand, next to a measurement-only term
+          auto sinc = ab::Polynomial<1>(100.) + ab::SquaredExponential<ab::EuclideanDistance>(3.5, 5.7) +
+                      ab::measurement_only(ab::IndependentNoise<double>(1.0));
+          auto fit2 = ab::gp_from_covariance(sinc).fit(d);
+          (void)fit2.predict(std::vector<double>{1.5}).joint();
         }""", tmp_path)
     assert ok.returncode == 0, ok.stderr
 
@@ -74,6 +79,11 @@ def test_supported_program_compiles(tmp_path):
           std::vector<std::array<double, 3>> xs(2);
           (void)n(xs);
         }""", "not defined for these feature types"),
+    # a Polynomial as a factor of a product (the device adds polynomial terms to the finished matrix: summands only)
+    ("""void f() {
+          auto cov = ab::Polynomial<1>(1.) * ab::SquaredExponential<ab::EuclideanDistance>(1., 1.);
+          (void)cov;
+        }""", "a Polynomial inside a product has no device form"),
     # a distance metric without a device form
     ("""struct AngularDistance { std::string get_name() const { return "angular"; } };
         void f() { ab::Exponential<AngularDistance> e; (void)e; }""", "only EuclideanDistance has a device form"),
